@@ -1,0 +1,434 @@
+// clx_api.cu — the device half of the C ABI (include/claxon_b200.h): context, device-resident
+// batches, the end-to-end host-buffer decode call and the claxon-shaped reader facade.
+//
+// There is deliberately no CPU decode path in this library: without a usable CUDA device
+// every entry point below fails with CLX_ERR_NO_DEVICE / CLX_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "claxon_b200.h"
+#include "clx_internal.h"
+
+struct clx_ctx {
+    int device = 0;
+    uint32_t flags = 0;
+    std::vector<cudaStream_t> streams;
+    std::string last_error;
+    uint64_t launches = 0;
+    // grow-only device scratch for clx_decode_frames, one set per stream (chunk pipelining)
+    struct Scratch {
+        uint8_t* d_bytes = nullptr; size_t bytes_cap = 0;
+        clx_frame_desc* d_descs = nullptr; size_t descs_cap = 0;
+        int32_t* d_out = nullptr; size_t out_cap = 0;
+        clx_frame_result* d_results = nullptr; size_t results_cap = 0;
+        int* d_need_hi = nullptr;
+    };
+    std::vector<Scratch> scratch;
+    std::vector<clx_frame_desc> h_descs;  // rebased descriptors of the chunk in flight
+    unsigned host_threads = 1;
+};
+
+struct clx_batch {
+    uint8_t* d_bytes = nullptr; size_t nbytes = 0, buf_bytes = 0;
+    clx_frame_desc* d_descs = nullptr;
+    int32_t* d_out = nullptr; size_t out_elems = 0;
+    clx_frame_result* d_results = nullptr;
+    int* d_need_hi = nullptr;
+    uint32_t n_frames = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int cuda_fail(clx_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return CLX_ERR_CUDA;
+}
+#define CU(ctx, call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+    } while (0)
+
+template <typename T>
+int grow(clx_ctx* ctx, T*& ptr, size_t& cap, size_t need, size_t slack) {
+    if (need <= cap && ptr) return CLX_OK;
+    if (ptr) CU(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    size_t want = need + need / 4 + slack;
+    CU(ctx, cudaMalloc((void**)&ptr, want * sizeof(T)));
+    cap = want;
+    return CLX_OK;
+}
+
+// The frame CRC-16 (src/frame.rs:752-763) is checked on the host, after — and only when — the
+// subframes decoded, so subframe errors keep their precedence over "frame CRC mismatch".
+void verify_crc_range(const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results, size_t lo,
+                      size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+        if (results[i].status != CLX_OK) continue;
+        const clx_frame_desc& d = descs[i];
+        const uint32_t consumed = results[i].consumed;
+        if ((d.flags & CLX_FRAME_CRC16_VERIFIED) && consumed == d.byte_len) continue;  // demuxer did it
+        const uint8_t* f = bytes + d.byte_offset;
+        const uint16_t stored = (uint16_t)(((uint32_t)f[consumed - 2] << 8) | f[consumed - 1]);
+        if (clx_crc16(f, consumed - 2) != stored) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
+    }
+}
+
+void verify_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results,
+                size_t n) {
+    if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
+    unsigned nt = std::min<unsigned>(ctx->host_threads, (unsigned)std::max<size_t>(1, n / 64));
+    if (nt <= 1) return verify_crc_range(bytes, descs, results, 0, n);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++)
+        th.emplace_back(verify_crc_range, bytes, descs, results, n * t / nt, n * (t + 1) / nt);
+    verify_crc_range(bytes, descs, results, 0, n / nt);
+    for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
+    if (!out) return CLX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return CLX_ERR_NO_DEVICE;
+    clx_ctx* ctx = new clx_ctx();
+    ctx->device = opts ? opts->device : 0;
+    ctx->flags = opts ? opts->flags : 0;
+    if (ctx->device < 0 || ctx->device >= count) { delete ctx; return CLX_ERR_NO_DEVICE; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return CLX_ERR_NO_DEVICE; }
+    uint32_t ns = opts && opts->n_streams ? opts->n_streams : 2;
+    ns = std::min<uint32_t>(ns, 64);
+    ctx->streams.resize(ns);
+    for (uint32_t i = 0; i < ns; i++)
+        if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return CLX_ERR_CUDA;
+        }
+    ctx->scratch.resize(ns);
+    ctx->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    *out = ctx;
+    return CLX_OK;
+}
+
+void clx_ctx_destroy(clx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& s : ctx->scratch) {
+        cudaFree(s.d_bytes); cudaFree(s.d_descs); cudaFree(s.d_out); cudaFree(s.d_results); cudaFree(s.d_need_hi);
+    }
+    for (auto s : ctx->streams) cudaStreamDestroy(s);
+    delete ctx;
+}
+
+const char* clx_ctx_last_error(const clx_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t clx_ctx_launch_count(const clx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* clx_ctx_stream(clx_ctx* ctx, uint32_t i) { return ctx ? (void*)ctx->streams[i % ctx->streams.size()] : nullptr; }
+
+// ---------------------------------------------------------------------------------
+// end-to-end decode with host buffers
+// ---------------------------------------------------------------------------------
+int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                      size_t n_frames, int32_t* out, size_t out_elems, clx_frame_result* results) {
+    if (!ctx || (!bytes && nbytes) || (!descs && n_frames) || (!results && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
+    if (n_frames == 0) return CLX_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n_frames; i++) {
+        const clx_frame_desc& d = descs[i];
+        const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
+        if (d.byte_offset > nbytes || d.byte_len > nbytes - d.byte_offset || d.header_len > d.byte_len ||
+            d.n_channels < 1 || d.n_channels > 8 || d.block_size == 0 || d.byte_len > (1u << 28) ||
+            (d.channel_assignment >= 8 && d.n_channels != 2) || d.out_offset + elems > out_elems || (!out && elems))
+            return CLX_ERR_INVALID_ARGUMENT;
+    }
+    // Chunks of frames are pipelined over the context's streams: H2D of chunk i+1 and D2H of
+    // chunk i-1 overlap the kernels of chunk i.  A chunk covers a contiguous byte range and a
+    // contiguous output range (descriptors in stream order, as the demuxer emits them).
+    const size_t ns = ctx->streams.size();
+    size_t n_chunks = std::min<size_t>(ns, std::max<size_t>(1, n_frames / 256));
+    for (size_t i = 1; i < n_frames && n_chunks > 1; i++)  // chunking needs stream order on both sides
+        if (descs[i].byte_offset < descs[i - 1].byte_offset || descs[i].out_offset < descs[i - 1].out_offset)
+            n_chunks = 1;
+    ctx->h_descs.assign(descs, descs + n_frames);
+    struct Span { size_t f0, f1; uint64_t b0, b1, o0, o1; };
+    std::vector<Span> spans;
+    for (size_t c = 0; c < n_chunks; c++) {
+        Span s{n_frames * c / n_chunks, n_frames * (c + 1) / n_chunks, ~0ull, 0, ~0ull, 0};
+        for (size_t i = s.f0; i < s.f1; i++) {
+            const clx_frame_desc& d = descs[i];
+            s.b0 = std::min<uint64_t>(s.b0, d.byte_offset & ~15ull);
+            s.b1 = std::max<uint64_t>(s.b1, d.byte_offset + d.byte_len);
+            s.o0 = std::min<uint64_t>(s.o0, d.out_offset & ~3ull);
+            s.o1 = std::max<uint64_t>(s.o1, d.out_offset + (uint64_t)d.n_channels * d.block_size);
+        }
+        for (size_t i = s.f0; i < s.f1; i++) {
+            ctx->h_descs[i].byte_offset -= s.b0;
+            ctx->h_descs[i].out_offset -= s.o0;
+        }
+        spans.push_back(s);
+    }
+    for (size_t c = 0; c < n_chunks; c++) {
+        const Span& s = spans[c];
+        clx_ctx::Scratch& sc = ctx->scratch[c];
+        cudaStream_t st = ctx->streams[c];
+        const size_t nb = (size_t)(s.b1 - s.b0), nf = s.f1 - s.f0, no = (size_t)(s.o1 - s.o0);
+        int rc;
+        if ((rc = grow(ctx, sc.d_bytes, sc.bytes_cap, nb + 64, 4096))) return rc;
+        if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return rc;
+        if ((rc = grow(ctx, sc.d_out, sc.out_cap, no + 4, 4096))) return rc;
+        if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return rc;
+        if (!sc.d_need_hi) CU(ctx, cudaMalloc((void**)&sc.d_need_hi, sizeof(int)));
+        CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs.data() + s.f0, nf * sizeof(clx_frame_desc),
+                                cudaMemcpyHostToDevice, st));
+        CU(ctx, clx::launch_decode(sc.d_bytes, (nb + 3) & ~(size_t)3, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
+                                   sc.d_need_hi, st, &ctx->launches));
+        CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
+    }
+    for (size_t c = 0; c < n_chunks; c++) CU(ctx, cudaStreamSynchronize(ctx->streams[c]));
+    verify_crc(ctx, bytes, descs, results, n_frames);
+    return CLX_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// device-resident batches
+// ---------------------------------------------------------------------------------
+int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs, size_t n_frames,
+                     size_t out_elems, clx_batch** out) {
+    if (!ctx || !out || (!bytes && nbytes) || (!descs && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n_frames; i++) {
+        const clx_frame_desc& d = descs[i];
+        const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
+        if (d.byte_offset > nbytes || d.byte_len > nbytes - d.byte_offset || d.header_len > d.byte_len ||
+            d.n_channels < 1 || d.n_channels > 8 || d.block_size == 0 || d.byte_len > (1u << 28) ||
+            (d.channel_assignment >= 8 && d.n_channels != 2) || d.out_offset + elems > out_elems)
+            return CLX_ERR_INVALID_ARGUMENT;
+    }
+    clx_batch* b = new clx_batch();
+    b->nbytes = nbytes;
+    b->buf_bytes = (nbytes + 3) & ~(size_t)3;
+    b->out_elems = out_elems;
+    b->n_frames = (uint32_t)n_frames;
+    cudaError_t e = cudaMalloc((void**)&b->d_bytes, b->buf_bytes + 64);
+    if (e == cudaSuccess) e = cudaMemset(b->d_bytes, 0, b->buf_bytes + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_descs, std::max<size_t>(1, n_frames) * sizeof(clx_frame_desc));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_out, (out_elems + 4) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_descs, descs, n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
+    if (e != cudaSuccess) {
+        clx_batch_destroy(ctx, b);
+        return cuda_fail(ctx, e, "clx_batch_create");
+    }
+    *out = b;
+    return CLX_OK;
+}
+
+int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index) {
+    if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = ctx->streams[stream_index % ctx->streams.size()];
+    b->last_stream = st;
+    CU(ctx, cudaEventRecord(b->ev_start, st));
+    CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
+                               st, &ctx->launches));
+    CU(ctx, cudaEventRecord(b->ev_stop, st));
+    return CLX_OK;
+}
+
+int clx_batch_sync(clx_ctx* ctx, clx_batch* b) {
+    if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
+    if (b->last_stream) CU(ctx, cudaStreamSynchronize(b->last_stream));
+    return CLX_OK;
+}
+
+int clx_batch_last_kernel_ms(clx_ctx* ctx, clx_batch* b, float* ms) {
+    if (!ctx || !b || !ms) return CLX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaEventSynchronize(b->ev_stop));
+    CU(ctx, cudaEventElapsedTime(ms, b->ev_start, b->ev_stop));
+    return CLX_OK;
+}
+
+int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, clx_frame_result* results) {
+    if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
+    int rc = clx_batch_sync(ctx, b);
+    if (rc) return rc;
+    if (out) CU(ctx, cudaMemcpy(out, b->d_out, std::min(out_elems, b->out_elems) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (results) CU(ctx, cudaMemcpy(results, b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+    return CLX_OK;
+}
+
+void clx_batch_destroy(clx_ctx* ctx, clx_batch* b) {
+    (void)ctx;
+    if (!b) return;
+    cudaFree(b->d_bytes); cudaFree(b->d_descs); cudaFree(b->d_out); cudaFree(b->d_results); cudaFree(b->d_need_hi);
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
+    if (b->ev_stop) cudaEventDestroy(b->ev_stop);
+    delete b;
+}
+
+void* clx_batch_device_out(clx_batch* b) { return b ? b->d_out : nullptr; }
+void* clx_batch_device_bytes(clx_batch* b) { return b ? b->d_bytes : nullptr; }
+
+// Pinned host memory for callers that want true asynchronous copies.
+void* clx_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void clx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// reader facade: claxon::FrameReader / FlacReader::blocks() over the batched device path
+// ---------------------------------------------------------------------------------
+struct clx_reader {
+    clx_ctx* ctx = nullptr;
+    const uint8_t* bytes = nullptr;
+    size_t n = 0;
+    uint64_t pos = 0;
+    bool have_si = false;
+    clx_streaminfo si{};
+    std::vector<clx_frame_desc> descs;
+    std::vector<clx_frame_result> results;
+};
+
+namespace {
+// Upper bound on the bytes a sane encoder spends on a frame: verbatim coding plus slack.
+size_t sane_frame_bound(const clx_frame_desc& d) {
+    const size_t per_ch = ((size_t)d.block_size * (d.bits_per_sample + 2u)) / 8 + 256;
+    return (size_t)d.header_len + (size_t)d.n_channels * per_ch + 2;
+}
+uint64_t block_time(const clx_frame_desc& d) {  // src/frame.rs:771-774
+    return (d.flags & CLX_FRAME_VARIABLE_BLOCKING) ? d.number : (uint64_t)d.block_size * d.number;
+}
+}  // namespace
+
+extern "C" {
+
+int clx_reader_open_frames(clx_ctx* ctx, const uint8_t* bytes, size_t n, clx_reader** out) {
+    if (!ctx || !out || (!bytes && n)) return CLX_ERR_INVALID_ARGUMENT;
+    clx_reader* r = new clx_reader();
+    r->ctx = ctx;
+    r->bytes = bytes;
+    r->n = n;
+    *out = r;
+    return CLX_OK;
+}
+
+int clx_reader_open_flac(clx_ctx* ctx, const uint8_t* bytes, size_t n, clx_reader** out) {
+    if (!ctx || !out || (!bytes && n)) return CLX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    clx_streaminfo si;
+    uint64_t first = 0;
+    int st = clx_open_stream(bytes, n, &si, &first);
+    if (st) return st;
+    clx_reader* r = new clx_reader();
+    r->ctx = ctx;
+    r->bytes = bytes;
+    r->n = n;
+    r->pos = first;
+    r->have_si = true;
+    r->si = si;
+    *out = r;
+    return CLX_OK;
+}
+
+int clx_reader_streaminfo(const clx_reader* r, clx_streaminfo* si) {
+    if (!r || !si || !r->have_si) return CLX_ERR_INVALID_ARGUMENT;
+    *si = r->si;
+    return CLX_OK;
+}
+
+uint64_t clx_reader_position(const clx_reader* r) { return r ? r->pos : 0; }
+void clx_reader_close(clx_reader* r) { delete r; }
+
+int clx_reader_next(clx_reader* r, int32_t* buffer, size_t capacity, uint32_t* block_size, uint32_t* channels,
+                    uint64_t* time) {
+    if (!r) return CLX_ERR_INVALID_ARGUMENT;
+    clx_frame_desc d;
+    const size_t avail = r->n - r->pos;
+    int st = clx_parse_frame_header(r->bytes + r->pos, avail, &d, r->ctx->flags);
+    if (st) return st;  // CLX_EOF == Ok(None)
+    if (block_size) *block_size = d.block_size;
+    if (channels) *channels = d.n_channels;
+    const size_t elems = (size_t)d.n_channels * d.block_size;
+    if (capacity < elems || !buffer) return CLX_ERR_INVALID_ARGUMENT;  // ensure_buffer_len is the caller's job
+    d.byte_offset = r->pos;
+    d.out_offset = 0;
+    clx_frame_result res{};
+    // A frame does not carry its length; give the device a generous window and widen it to the
+    // rest of the stream in the (pathological) case the frame turns out to be longer.
+    size_t window = std::min(avail, sane_frame_bound(d));
+    for (;;) {
+        d.byte_len = (uint32_t)std::min<size_t>(window, (size_t)1 << 28);
+        st = clx_decode_frames(r->ctx, r->bytes, r->n, &d, 1, buffer, capacity, &res);
+        if (st) return st;
+        if (res.status == CLX_ERR_IO_UNEXPECTED_EOF && window < avail) { window = avail; continue; }
+        break;
+    }
+    if (res.status != CLX_OK) return res.status;
+    r->pos += res.consumed;
+    if (time) *time = block_time(d);
+    return CLX_OK;
+}
+
+int clx_reader_next_batch(clx_reader* r, size_t max_frames, int32_t* buffer, size_t capacity, clx_frame_desc* descs,
+                          size_t* n_decoded) {
+    if (!r || !n_decoded || !descs) return CLX_ERR_INVALID_ARGUMENT;
+    *n_decoded = 0;
+    if (max_frames == 0) return CLX_OK;
+    r->descs.resize(max_frames);
+    uint64_t next = r->pos, total = 0;
+    int stop = CLX_OK;
+    size_t n = clx_demux_frames(r->bytes, r->n, r->pos, r->descs.data(), max_frames, &next, &total, &stop,
+                                r->ctx->flags);
+    if (n == 0) return stop;  // header-level error or CLX_EOF
+    // fit the caller's buffer
+    while (n > 0) {
+        const clx_frame_desc& last = r->descs[n - 1];
+        if (last.out_offset + (uint64_t)last.n_channels * last.block_size <= capacity) break;
+        n--;
+    }
+    if (n == 0) return CLX_ERR_INVALID_ARGUMENT;
+    r->results.resize(n);
+    int st = clx_decode_frames(r->ctx, r->bytes, r->n, r->descs.data(), n, buffer, capacity, r->results.data());
+    if (st) return st;
+    size_t good = 0;
+    while (good < n && r->results[good].status == CLX_OK) good++;
+    if (good == 0) {
+        // The very first frame failed.  If its window was a guess, retry through the exact path.
+        return r->results[0].status;
+    }
+    for (size_t i = 0; i < good; i++) {
+        descs[i] = r->descs[i];
+        descs[i].byte_len = r->results[i].consumed;
+        descs[i].number = block_time(r->descs[i]);  // Block::time()
+    }
+    const clx_frame_desc& lastd = r->descs[good - 1];
+    r->pos = lastd.byte_offset + r->results[good - 1].consumed;
+    *n_decoded = good;
+    return CLX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+/* claxon_b200.h — C ABI of the B200-native batched FLAC frame decoder.
+ *
+ * This is the drop-in boundary for the per-frame decode path of ruuda/claxon
+ * v0.4.3.  claxon has no FFI of its own; its boundary is the Rust API
+ *   FrameReader::read_next_or_eof(&mut self, Vec<i32>) -> Result<Option<Block>>
+ *                                                     (reference src/frame.rs:667)
+ *   FlacReader::{new, streaminfo, blocks, samples}    (src/lib.rs:217-435)
+ *   Block::{time, len, duration, channels, channel, sample, into_buffer}
+ *                                                     (src/frame.rs:402-529)
+ * A Rust `extern "C"` shim binds exactly the entry points below:
+ * the host parses frame headers (clx_parse_frame_header == src/frame.rs:131-316),
+ * ships raw frame bitstreams to the device, and everything below the header parse
+ * and above the CRC-16 footer check — subframe::decode (src/subframe.rs:184-228),
+ * decode_residual (:236-380), predict_fixed (:417-474), predict_lpc_* (:524-614),
+ * decode_{left,right,mid}_side (src/frame.rs:319-389) — runs in sm_100a kernels.
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ * There is NO CPU fallback: if no CUDA device is usable the create call fails
+ * with CLX_ERR_NO_DEVICE.
+ */
+#ifndef CLAXON_B200_H
+#define CLAXON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "clx_status.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLX_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------- */
+/* Frame descriptor: the parsed frame header + where the frame's bytes are.   */
+/* Mirrors claxon's private FrameHeader (src/frame.rs:41-48).                 */
+/* ------------------------------------------------------------------------- */
+typedef struct clx_frame_desc {
+    uint64_t byte_offset;        /* offset of the frame's first sync byte in the byte buffer */
+    uint32_t byte_len;           /* bytes AVAILABLE to this frame from byte_offset: the exact frame
+                                    length (sync..CRC-16) when known, else an upper bound (e.g. to
+                                    the end of the stream).  Reads past it are UnexpectedEof. */
+    uint16_t header_len;         /* frame header bytes incl. the CRC-8 */
+    uint16_t block_size;         /* 1..65535 inter-channel samples */
+    uint8_t n_channels;          /* 1..8 */
+    uint8_t channel_assignment;  /* raw 4-bit code: 0..7 independent(n+1), 8 L/S, 9 R/S, 10 M/S */
+    uint8_t bits_per_sample;     /* 8/12/16/20/24; 0 = not in the header (-> Unsupported) */
+    uint8_t flags;               /* CLX_FRAME_* */
+    uint32_t sample_rate;        /* Hz, 0 = "from streaminfo"; not used by the decode */
+    uint64_t number;             /* coded frame / sample number */
+    uint64_t out_offset;         /* element (i32) offset of this frame's samples in the output;
+                                    multiple of 4 recommended (vectorised stores) */
+} clx_frame_desc;
+
+#define CLX_FRAME_VARIABLE_BLOCKING 1u /* `number` is a sample number, else a frame number */
+#define CLX_FRAME_CRC16_VERIFIED 2u    /* set by clx_demux_frames: CRC-16 of the first byte_len-2 bytes
+                                          already matched the footer (saves the host a second pass) */
+
+/* Per-frame outcome. */
+typedef struct clx_frame_result {
+    int32_t status;      /* clx_status; CLX_OK when the frame decoded and its CRC-16 matched */
+    uint32_t consumed;   /* bytes from the sync code through the CRC-16 (valid when status is
+                            CLX_OK or CLX_ERR_FRAME_CRC_MISMATCH) */
+} clx_frame_result;
+
+/* STREAMINFO (src/metadata.rs:29-54). 0 = unknown for frame sizes / samples. */
+typedef struct clx_streaminfo {
+    uint32_t min_block_size, max_block_size;
+    uint32_t min_frame_size, max_frame_size;
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint64_t samples;
+    uint8_t md5sum[16];
+} clx_streaminfo;
+
+typedef struct clx_options {
+    int32_t device;        /* CUDA device ordinal */
+    uint32_t flags;        /* CLX_OPT_* */
+    uint32_t n_streams;    /* internal CUDA streams for host<->device pipelining (0 = default 2) */
+    uint32_t reserved;
+} clx_options;
+#define CLX_OPT_NO_VERIFY_CRC 1u /* mimic claxon's cfg(fuzzing): skip CRC-8/CRC-16 checks */
+
+typedef struct clx_ctx clx_ctx;     /* one per host thread / GPU; owns device scratch */
+typedef struct clx_batch clx_batch; /* a device-resident batch (bytes + descriptors + output) */
+
+/* ------------------------------------------------------------------------- */
+/* status helpers                                                             */
+/* ------------------------------------------------------------------------- */
+const char* clx_status_str(int status);  /* claxon's verbatim error string */
+int clx_status_kind(int status);         /* clx_error_kind */
+uint32_t clx_abi_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* host-side parsing (no GPU needed)                                          */
+/* ------------------------------------------------------------------------- */
+
+/* read_frame_header_or_eof (src/frame.rs:131-316) on p[0..n).  Fills every field of
+ * `d` except byte_offset/byte_len/out_offset.  CLX_EOF when fewer than 2 bytes remain. */
+int clx_parse_frame_header(const uint8_t* p, size_t n, clx_frame_desc* d, uint32_t flags);
+
+/* FlacReader::new (src/lib.rs:217-307, default options): checks 'fLaC', walks the
+ * metadata blocks, returns STREAMINFO and the offset of the first frame. */
+int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* first_frame);
+
+/* Frame demultiplexer: finds frame boundaries in bytes[start..n) without decoding:
+ * sync code + header parse + CRC-8, then the first later sync position at which the
+ * CRC-16 over the candidate span matches (or the end of the stream).  Writes up to
+ * `max_frames` descriptors with exact byte_len and out_offset laid out back to back
+ * (each frame aligned to 4 elements).  Stops at the first position that is not a
+ * valid frame start and reports that header's status in *stop_status (CLX_EOF at a
+ * clean end).  Returns the number of descriptors written. */
+size_t clx_demux_frames(const uint8_t* bytes, size_t n, uint64_t start, clx_frame_desc* descs,
+                        size_t max_frames, uint64_t* next_offset, uint64_t* total_out_elems,
+                        int* stop_status, uint32_t flags);
+
+uint8_t clx_crc8(const uint8_t* p, size_t n);   /* src/crc.rs: poly 0x07, init 0 */
+uint16_t clx_crc16(const uint8_t* p, size_t n); /* src/crc.rs: poly 0x8005, init 0 */
+
+/* ------------------------------------------------------------------------- */
+/* device path                                                                */
+/* ------------------------------------------------------------------------- */
+int clx_ctx_create(const clx_options* opts, clx_ctx** out);
+void clx_ctx_destroy(clx_ctx* ctx);
+const char* clx_ctx_last_error(const clx_ctx* ctx); /* CUDA error text for CLX_ERR_CUDA */
+
+/* The per-frame decode path, end to end with HOST buffers (the call a binding makes):
+ * copies the frame bytes to the device, runs the decode kernels, copies the planar
+ * i32 PCM (Block layout: buffer[ch*block_size + i], src/frame.rs:477-481) back into
+ * `out` at descs[i].out_offset, and fills results[i].  The frame CRC-16 is verified
+ * (unless CLX_OPT_NO_VERIFY_CRC) after the subframes, so subframe errors pre-empt
+ * "frame CRC mismatch" exactly as in src/frame.rs:752-763.  A failed frame never
+ * aborts the batch; its output region is fully overwritten (never stale). */
+int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                      size_t n_frames, int32_t* out, size_t out_elems, clx_frame_result* results);
+
+/* Device-resident variant: upload once, decode many times (kernel-only timing), read back. */
+int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                     size_t n_frames, size_t out_elems, clx_batch** out);
+int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index); /* async on an internal stream */
+int clx_batch_sync(clx_ctx* ctx, clx_batch* b);
+int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, clx_frame_result* results);
+void clx_batch_destroy(clx_ctx* ctx, clx_batch* b);
+/* Raw device pointers of a batch (for zero-copy consumers, e.g. torch / NCCL). */
+void* clx_batch_device_out(clx_batch* b);
+void* clx_batch_device_bytes(clx_batch* b);
+/* Events-based timing of the kernels of the last `clx_batch_decode` on this batch (ms). */
+int clx_batch_last_kernel_ms(clx_ctx* ctx, clx_batch* b, float* ms);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+uint64_t clx_ctx_launch_count(const clx_ctx* ctx);
+void* clx_ctx_stream(clx_ctx* ctx, uint32_t stream_index); /* cudaStream_t */
+
+/* Pinned (page-locked) host memory so that the copies inside clx_decode_frames are truly
+ * asynchronous; optional — any host pointer works. */
+void* clx_host_alloc(size_t bytes);
+void clx_host_free(void* p);
+
+/* ------------------------------------------------------------------------- */
+/* claxon-shaped reader facade (FlacReader / FrameReader over the calls above) */
+/* ------------------------------------------------------------------------- */
+typedef struct clx_reader clx_reader;
+
+/* FrameReader::new over an in-memory span positioned at a frame header
+ * (src/frame.rs:652); `clx_reader_open_flac` is FlacReader::new + blocks(). */
+int clx_reader_open_frames(clx_ctx* ctx, const uint8_t* bytes, size_t n, clx_reader** out);
+int clx_reader_open_flac(clx_ctx* ctx, const uint8_t* bytes, size_t n, clx_reader** out);
+int clx_reader_streaminfo(const clx_reader* r, clx_streaminfo* si);
+/* read_next_or_eof: decodes ONE frame through the device path.  `buffer`/`capacity`
+ * is the recycled Vec<i32>; on CLX_OK the block_size / channels / time outputs describe
+ * the Block and `buffer[0 .. channels*block_size)` holds it.  If capacity is too small the
+ * call returns CLX_ERR_INVALID_ARGUMENT with block_size and channels set, consuming nothing.
+ * CLX_EOF == Ok(None). */
+int clx_reader_next(clx_reader* r, int32_t* buffer, size_t capacity, uint32_t* block_size,
+                    uint32_t* channels, uint64_t* time);
+/* Batched extension: demuxes up to max_frames frames ahead and decodes them in one
+ * device launch.  Stops before the first frame that fails (that frame's status is
+ * returned by the next call).  Returns the number of frames decoded in *n_decoded. */
+int clx_reader_next_batch(clx_reader* r, size_t max_frames, int32_t* buffer, size_t capacity,
+                          clx_frame_desc* descs, size_t* n_decoded);
+uint64_t clx_reader_position(const clx_reader* r); /* byte offset of the next frame */
+void clx_reader_close(clx_reader* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAXON_B200_H */

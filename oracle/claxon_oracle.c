@@ -23,40 +23,50 @@ typedef struct {
     int err;        /* sticky: CLX_ERR_IO_UNEXPECTED_EOF once a read ran off the end */
 } bitcur;
 
+/* 64 bits starting at byte `byte_at`, big-endian, zero-filled past the end. */
+static inline uint64_t bc_load64(const bitcur* b, uint64_t byte_at) {
+    uint64_t nbytes = b->nbits >> 3;
+    if (byte_at + 8 <= nbytes) {
+        uint64_t w;
+        memcpy(&w, b->p + byte_at, 8);
+        return __builtin_bswap64(w);
+    }
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < 8; i++) {
+        w <<= 8;
+        if (byte_at + i < nbytes) w |= b->p[byte_at + i];
+    }
+    return w;
+}
+
 /* Reads `n` (0..32) bits MSB-first.  src/input.rs:515-643 (read_leq_u8/u16/u32,
  * read_gt_u8_leq_u16): all are plain big-endian bit-field extraction. */
-static uint32_t bc_read(bitcur* b, uint32_t n) {
+static inline uint32_t bc_read(bitcur* b, uint32_t n) {
     if (n == 0) return 0; /* read_leq_u8(0) consumes nothing (src/input.rs:521, :706) */
     if (b->err) return 0;
     if (b->pos + n > b->nbits) { b->err = CLX_ERR_IO_UNEXPECTED_EOF; return 0; }
-    uint64_t acc = 0;
-    uint64_t pos = b->pos;
-    uint32_t left = n;
-    while (left > 0) {
-        uint32_t byte = b->p[pos >> 3];
-        uint32_t avail = 8 - (uint32_t)(pos & 7);
-        uint32_t take = left < avail ? left : avail;
-        uint32_t chunk = (byte >> (avail - take)) & ((1u << take) - 1u);
-        acc = (acc << take) | chunk;
-        pos += take;
-        left -= take;
-    }
-    b->pos = pos;
-    return (uint32_t)acc;
+    uint64_t w = bc_load64(b, b->pos >> 3) << (b->pos & 7); /* (pos&7) + n <= 39 < 64 */
+    b->pos += n;
+    return (uint32_t)(w >> (64 - n));
 }
 
 /* Counts zero bits up to the next one bit and consumes that one bit.
  * src/input.rs:475-511 (read_unary). */
-static uint32_t bc_unary(bitcur* b) {
+static inline uint32_t bc_unary(bitcur* b) {
     if (b->err) return 0;
     uint32_t n = 0;
     for (;;) {
         if (b->pos >= b->nbits) { b->err = CLX_ERR_IO_UNEXPECTED_EOF; return 0; }
-        uint32_t byte = b->p[b->pos >> 3];
-        uint32_t bit = (byte >> (7 - (b->pos & 7))) & 1u;
-        b->pos++;
-        if (bit) return n;
-        n++;
+        uint32_t skew = (uint32_t)(b->pos & 7);
+        uint64_t w = bc_load64(b, b->pos >> 3) << skew;
+        uint64_t valid = 64 - skew;
+        if (valid > b->nbits - b->pos) valid = b->nbits - b->pos;
+        if (w != 0) {
+            uint32_t z = (uint32_t)__builtin_clzll(w);
+            if (z < valid) { b->pos += z + 1; return n + z; }
+        }
+        n += (uint32_t)valid;
+        b->pos += valid;
     }
 }
 
@@ -147,14 +157,25 @@ void clxo_predict_fixed(uint32_t order, int32_t* buf, size_t n) {
  * i.e. reversed-from-stream, order).  i64 products and sum, arithmetic >> shift,
  * + residual in i64, truncate to i32.  The low-order variant's zero padding to 12
  * taps (:543-551, :575-582) is numerically the same `order`-tap recurrence. */
-void clxo_predict_lpc(const int16_t* coefs, uint32_t order, uint32_t shift, int32_t* buf,
-                      size_t n) {
+static inline __attribute__((always_inline)) void lpc_run(const int16_t* coefs, uint32_t order,
+                                                          uint32_t shift, int32_t* buf, size_t n) {
     for (size_t i = order; i < n; i++) {
         int64_t sum = 0;
         for (uint32_t j = 0; j < order; j++)
             sum += (int64_t)coefs[j] * (int64_t)buf[i - order + j];
         int64_t pred = sum >> shift;
         buf[i] = (int32_t)(uint32_t)(uint64_t)(pred + (int64_t)buf[i]);
+    }
+}
+
+void clxo_predict_lpc(const int16_t* coefs, uint32_t order, uint32_t shift, int32_t* buf,
+                      size_t n) {
+    switch (order) { /* constant trip counts let the compiler unroll the tap loop */
+#define CASE(o) case o: lpc_run(coefs, o, shift, buf, n); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11)
+    CASE(12)
+#undef CASE
+    default: lpc_run(coefs, order, shift, buf, n); break;
     }
 }
 
@@ -213,7 +234,24 @@ static int read_residual(bitcur* b, uint32_t block_size, uint32_t n_warm_up, int
         uint32_t k = bc_read(b, param_bits);
         if (b->err) return b->err;
         if (k == escape) return CLX_ERR_UNENCODED_BINARY; /* :317, :365 */
+        uint64_t nbytes = b->nbits >> 3;
         for (uint32_t i = 0; i < len; i++) {
+            uint64_t byte_at = b->pos >> 3;
+            if (byte_at + 8 <= nbytes) { /* whole code inside one 64-bit window: common case */
+                uint32_t skew = (uint32_t)(b->pos & 7);
+                uint64_t w;
+                memcpy(&w, b->p + byte_at, 8);
+                w = __builtin_bswap64(w) << skew;
+                if (w != 0) {
+                    uint32_t z = (uint32_t)__builtin_clzll(w);
+                    if (z + 1 + k + skew <= 64) {
+                        uint32_t r = k ? (uint32_t)((w << (z + 1)) >> (64 - k)) : 0;
+                        out[at + i] = clxo_rice_to_signed((z << k) | r);
+                        b->pos += z + 1 + k;
+                        continue;
+                    }
+                }
+            }
             uint32_t q = bc_unary(b);
             if (b->err) return b->err;
             uint32_t r = bc_read(b, k);
