@@ -207,6 +207,23 @@ class Context:
         _check(self._L.clx_decode_frames(self._h, bytes_ptr, nbytes, descs_ptr, n, out_ptr, out_elems,
                                          results_ptr), self)
 
+    def run_steps(self, batches: list["DeviceBatch"], steps: int, n_streams: int) -> float:
+        """Decodes `steps` batches round-robin over `n_streams` streams; returns device ms (CUDA events)."""
+        arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+        ms = C.c_float(0)
+        _check(self._L.clx_ctx_run_steps(self._h, arr, len(batches), steps, n_streams, C.byref(ms)), self)
+        return float(ms.value)
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Pinned host buffer as a uint8 ndarray (freed with host_free)."""
+        p = self._L.clx_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("cudaHostAlloc failed")
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p))
+
+    def host_free(self, arr: np.ndarray):
+        self._L.clx_host_free(arr.ctypes.data)
+
     def upload(self, data, descs: np.ndarray, out_elems: int) -> "DeviceBatch":
         return DeviceBatch(self, data, descs, out_elems)
 

@@ -78,5 +78,5 @@ def build_synth(force: bool = False) -> str:
         if os.path.exists(SYNTH):
             return SYNTH
         raise RuntimeError("gcc not found and no prebuilt libclxsynth.so")
-    subprocess.check_call([gcc, "-O2", "-fPIC", "-shared", "-o", SYNTH, src, "-lm"])
+    subprocess.check_call([gcc, "-O2", "-fPIC", "-shared", "-o", SYNTH, src, "-lm", "-lpthread"])
     return SYNTH

@@ -69,6 +69,7 @@ SYMBOLS = {
     "clx_batch_device_out": (_vp, [_vp]),
     "clx_batch_device_bytes": (_vp, [_vp]),
     "clx_batch_last_kernel_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
+    "clx_ctx_run_steps": (C.c_int, [_vp, C.POINTER(_vp), _sz, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "clx_ctx_launch_count": (C.c_uint64, [_vp]),
     "clx_ctx_stream": (_vp, [_vp, C.c_uint32]),
     "clx_host_alloc": (_vp, [_sz]),

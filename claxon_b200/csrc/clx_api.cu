@@ -286,6 +286,42 @@ void clx_batch_destroy(clx_ctx* ctx, clx_batch* b) {
     delete b;
 }
 
+// Decodes `steps` batches back to back, step i taking batches[i % n_batches] on internal stream
+// i % n_streams, and returns the device time (CUDA events) from the first launch to the last
+// completion.  This is the steady-state "many batches in flight" regime of a decode service.
+int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint32_t steps, uint32_t n_streams,
+                      float* total_ms) {
+    if (!ctx || !batches || n_batches == 0 || !total_ms) return CLX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    n_streams = std::max<uint32_t>(1, std::min<uint32_t>(n_streams, (uint32_t)ctx->streams.size()));
+    cudaEvent_t start, stop;
+    std::vector<cudaEvent_t> done(n_streams);
+    CU(ctx, cudaEventCreate(&start));
+    CU(ctx, cudaEventCreate(&stop));
+    for (auto& e : done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t s0 = ctx->streams[0];
+    CU(ctx, cudaEventRecord(start, s0));
+    for (uint32_t s = 1; s < n_streams; s++) CU(ctx, cudaStreamWaitEvent(ctx->streams[s], start, 0));
+    for (uint32_t i = 0; i < steps; i++) {
+        clx_batch* b = batches[i % n_batches];
+        cudaStream_t st = ctx->streams[i % n_streams];
+        b->last_stream = st;
+        CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
+                                   b->d_need_hi, st, &ctx->launches));
+    }
+    for (uint32_t s = 1; s < n_streams; s++) {
+        CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));
+        CU(ctx, cudaStreamWaitEvent(s0, done[s], 0));
+    }
+    CU(ctx, cudaEventRecord(stop, s0));
+    CU(ctx, cudaEventSynchronize(stop));
+    CU(ctx, cudaEventElapsedTime(total_ms, start, stop));
+    cudaEventDestroy(start);
+    cudaEventDestroy(stop);
+    for (auto& e : done) cudaEventDestroy(e);
+    return CLX_OK;
+}
+
 void* clx_batch_device_out(clx_batch* b) { return b ? b->d_out : nullptr; }
 void* clx_batch_device_bytes(clx_batch* b) { return b ? b->d_bytes : nullptr; }
 

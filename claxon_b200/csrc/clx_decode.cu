@@ -475,6 +475,30 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
 
     const uint32_t steps = __reduce_max_sync(0xffffffffu, L.total);
 
+    // Frame end (runs once per lane, as soon as its last sample has been produced — later the
+    // lane keeps executing the warp's instruction stream with its cursor running on garbage):
+    // last subframe's bookkeeping, then locate the CRC-16 footer.
+    bool finished = false;
+    auto finish_frame = [&]() {
+        finished = true;
+        if (L.status == CLX_OK) {
+            if (L.pred && !L.params_done) parse_params(L);  // last subframe had order == block size
+            if (L.status == CLX_OK && overrun(L)) L.status = CLX_ERR_IO_UNEXPECTED_EOF;
+        }
+        clx_frame_result res;
+        res.status = L.status;
+        res.consumed = 0;
+        if (L.status == CLX_OK) {
+            // Pad bits up to the byte boundary are skipped unchecked (src/frame.rs:744-750);
+            // the CRC-16 footer must still be readable (:754).
+            uint32_t end_bits = bc_pos(L.bc) - L.frame_bit0;
+            uint32_t end_byte = (end_bits + 7) >> 3;
+            if (end_byte + 2 > byte_len) res.status = CLX_ERR_IO_UNEXPECTED_EOF;
+            res.consumed = end_byte + 2;
+        }
+        results[fidx] = res;
+    };
+
     for (uint32_t it = 0; it < steps;) {
         // ------------------------------------------------------------------
         // events (rare, divergent): subframe boundaries, predictor parameters,
@@ -494,6 +518,7 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                 }
             }
         }
+        if (have && !finished && it >= L.total) finish_frame();
         // How many steps can this lane run before its next event?
         uint32_t run;
         if (it >= L.total) run = 0xffffffffu;
@@ -582,28 +607,7 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     // trailing partial tile
     if (steps & 31) flush_tile(tile, rows, steps & ~31u, lane);
 
-    // ------------------------------------------------------------------
-    // frame end: finish the last subframe's bookkeeping, find the footer
-    // ------------------------------------------------------------------
-    if (have) {
-        if (L.status == CLX_OK) {
-            if (L.pred && !L.params_done) parse_params(L);  // last subframe had order == block size
-            if (L.status == CLX_OK && (L.mode == M_VERB || L.mode == M_RICE || L.mode == M_CONST) && overrun(L))
-                L.status = CLX_ERR_IO_UNEXPECTED_EOF;
-        }
-        clx_frame_result res;
-        res.status = L.status;
-        res.consumed = 0;
-        if (L.status == CLX_OK) {
-            // Pad bits up to the byte boundary are skipped unchecked (src/frame.rs:744-750);
-            // the CRC-16 footer must still be readable (:754).
-            uint32_t end_bits = bc_pos(L.bc) - L.frame_bit0;
-            uint32_t end_byte = (end_bits + 7) >> 3;
-            if (end_byte + 2 > byte_len) res.status = CLX_ERR_IO_UNEXPECTED_EOF;
-            res.consumed = end_byte + 2;
-        }
-        results[fidx] = res;
-    }
+    if (have && !finished) finish_frame();
 }
 
 // ---------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
  * src/subframe.rs:317-319).  Plain C, no dependencies; not part of the decode path.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -419,7 +420,28 @@ static void gen_frame(const clxs_config* cfg, clxs_stream* s, uint32_t index, in
     put_byte(s, (uint8_t)c16);
 }
 
-clxs_stream* clxs_generate(const clxs_config* cfg) {
+typedef struct {
+    const clxs_config* cfg;
+    uint32_t lo, hi;
+    clxs_stream part;      /* bytes of frames [lo, hi) */
+    uint64_t* lens;        /* per-frame byte length */
+    int32_t* pcm;          /* global pcm buffer */
+    const uint64_t* pcm_offsets;
+} gen_job;
+
+static void* gen_worker(void* arg) {
+    gen_job* j = (gen_job*)arg;
+    int32_t* scratch = (int32_t*)malloc(sizeof(int32_t) * 65536);
+    for (uint32_t i = j->lo; i < j->hi; i++) {
+        size_t before = j->part.nbytes;
+        gen_frame(j->cfg, &j->part, i, j->pcm + j->pcm_offsets[i], scratch);
+        j->lens[i] = j->part.nbytes - before;
+    }
+    free(scratch);
+    return NULL;
+}
+
+clxs_stream* clxs_generate_mt(const clxs_config* cfg, int n_threads) {
     init_tabs();
     if (!cfg || cfg->n_channels < 1 || cfg->n_channels > 8 || cfg->block_size < 1 ||
         cfg->block_size > 65535)
@@ -442,17 +464,41 @@ clxs_stream* clxs_generate(const clxs_config* cfg) {
     s->pcm_offsets[cfg->n_frames] = total;
     s->n_samples = total;
     s->pcm = (int32_t*)malloc(sizeof(int32_t) * (size_t)(total ? total : 1));
-    int32_t* scratch = (int32_t*)malloc(sizeof(int32_t) * 65536);
-    s->cap = (size_t)(total * cfg->bps / 8 / 2) + 65536;
-    s->bytes = (uint8_t*)malloc(s->cap);
-    for (uint32_t i = 0; i < cfg->n_frames; i++) {
-        s->frame_offsets[i] = s->nbytes;
-        gen_frame(cfg, s, i, s->pcm + s->pcm_offsets[i], scratch);
+    if (n_threads < 1) n_threads = 1;
+    if ((uint32_t)n_threads > cfg->n_frames) n_threads = cfg->n_frames ? (int)cfg->n_frames : 1;
+    gen_job* jobs = (gen_job*)calloc((size_t)n_threads, sizeof(gen_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint64_t* lens = (uint64_t*)calloc((size_t)cfg->n_frames + 1, sizeof(uint64_t));
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t].cfg = cfg;
+        jobs[t].lo = (uint32_t)((uint64_t)cfg->n_frames * (uint64_t)t / (uint64_t)n_threads);
+        jobs[t].hi = (uint32_t)((uint64_t)cfg->n_frames * (uint64_t)(t + 1) / (uint64_t)n_threads);
+        jobs[t].lens = lens;
+        jobs[t].pcm = s->pcm;
+        jobs[t].pcm_offsets = s->pcm_offsets;
+        jobs[t].part.cap = (size_t)(total / (uint64_t)n_threads * cfg->bps / 8 / 2) + 65536;
+        jobs[t].part.bytes = (uint8_t*)malloc(jobs[t].part.cap);
+        if (t > 0) pthread_create(&th[t], NULL, gen_worker, &jobs[t]);
     }
-    s->frame_offsets[cfg->n_frames] = s->nbytes;
-    free(scratch);
+    gen_worker(&jobs[0]);
+    size_t nbytes = jobs[0].part.nbytes;
+    for (int t = 1; t < n_threads; t++) { pthread_join(th[t], NULL); nbytes += jobs[t].part.nbytes; }
+    s->bytes = (uint8_t*)malloc(nbytes + 64);
+    s->cap = nbytes + 64;
+    for (int t = 0; t < n_threads; t++) {
+        memcpy(s->bytes + s->nbytes, jobs[t].part.bytes, jobs[t].part.nbytes);
+        s->nbytes += jobs[t].part.nbytes;
+        free(jobs[t].part.bytes);
+    }
+    memset(s->bytes + s->nbytes, 0, 64);
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < cfg->n_frames; i++) { s->frame_offsets[i] = at; at += lens[i]; }
+    s->frame_offsets[cfg->n_frames] = at;
+    free(lens); free(jobs); free(th);
     return s;
 }
+
+clxs_stream* clxs_generate(const clxs_config* cfg) { return clxs_generate_mt(cfg, 1); }
 
 const uint8_t* clxs_bytes(const clxs_stream* s) { return s->bytes; }
 uint64_t clxs_nbytes(const clxs_stream* s) { return s->nbytes; }

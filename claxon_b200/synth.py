@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import os
 from dataclasses import dataclass, field, asdict
 
 import numpy as np
@@ -95,8 +96,8 @@ def _synth_lib():
     global _lib
     if _lib is None:
         L = C.CDLL(_build.build_synth())
-        L.clxs_generate.restype = C.c_void_p
-        L.clxs_generate.argtypes = [C.POINTER(_Cfg)]
+        L.clxs_generate_mt.restype = C.c_void_p
+        L.clxs_generate_mt.argtypes = [C.POINTER(_Cfg), C.c_int]
         for name, res in (("clxs_bytes", C.c_void_p), ("clxs_nbytes", C.c_uint64),
                           ("clxs_frame_offsets", C.c_void_p), ("clxs_pcm", C.c_void_p),
                           ("clxs_pcm_offsets", C.c_void_p), ("clxs_n_samples", C.c_uint64)):
@@ -115,10 +116,13 @@ def _copy(ptr: int, count: int, dtype) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=count).copy()
 
 
-def generate(cfg: SynthConfig) -> SynthBatch:
+def generate(cfg: SynthConfig, n_threads: int | None = None) -> SynthBatch:
+    """Deterministic in (cfg): frame i depends only on cfg.seed + i, whatever the thread count."""
     L = _synth_lib()
     c = _Cfg(**asdict(cfg))
-    h = L.clxs_generate(C.byref(c))
+    if n_threads is None:
+        n_threads = min(32, os.cpu_count() or 1)
+    h = L.clxs_generate_mt(C.byref(c), n_threads)
     if not h:
         raise ValueError("invalid synth config")
     try:

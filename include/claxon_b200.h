@@ -140,6 +140,11 @@ int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index); /* asyn
 int clx_batch_sync(clx_ctx* ctx, clx_batch* b);
 int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, clx_frame_result* results);
 void clx_batch_destroy(clx_ctx* ctx, clx_batch* b);
+/* Steady-state throughput: decodes `steps` batches back to back (step i = batches[i % n_batches]
+ * on internal stream i % n_streams, so several batches are in flight) and returns the device time
+ * from first launch to last completion, measured with CUDA events. */
+int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint32_t steps, uint32_t n_streams,
+                      float* total_ms);
 /* Raw device pointers of a batch (for zero-copy consumers, e.g. torch / NCCL). */
 void* clx_batch_device_out(clx_batch* b);
 void* clx_batch_device_bytes(clx_batch* b);

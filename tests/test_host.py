@@ -1,0 +1,260 @@
+"""Host-side logic of the product (no GPU): C ABI surface, header parse, CRC, metadata walk,
+demuxer, claxon-shaped Block API, error contract.  The oracle is used only as the checker."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import claxon_b200 as cb
+from claxon_b200 import _lib, synth, shard
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly the functions include/claxon_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "claxon_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(clx_[a-z0-9_]+)\s*\(", header))
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert L.clx_abi_version() == 1
+    # the CUDA kernels are in the same library (sm_100a SASS present)
+    out = subprocess.run(["cuobjdump", "-lelf", _lib._build.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "claxon_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".c", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "claxon_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the decode path must raise, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cb.Error) as e:
+        cb.Context()
+    assert e.value.status == 92
+
+
+def test_status_strings_match_claxon():
+    # verbatim strings, compared by string in the reference (src/error.rs:34-45)
+    expect = {3: "frame sync code missing", 9: "frame header CRC mismatch", 16: "invalid partition order",
+              18: "unencoded binary is not yet implemented", 23: "frame CRC mismatch",
+              10: "header without bits per sample info", 14: "subframe has no non-wasted bits",
+              22: "a negative quantized linear predictor coefficient shift is not supported, please file a bug.",
+              43: "vendor string too long", 30: "invalid stream header"}
+    for k, v in expect.items():
+        assert cb.status_str(k) == v
+    L = _lib.load()
+    assert L.clx_status_kind(10) == cb.KIND_UNSUPPORTED and L.clx_status_kind(18) == cb.KIND_UNSUPPORTED
+    assert L.clx_status_kind(2) == cb.KIND_IO and L.clx_status_kind(23) == cb.KIND_FORMAT
+
+
+def test_error_equality_semantics():
+    assert cb.Error(23) == cb.Error(23) and cb.Error(23) != cb.Error(9)
+    assert cb.Error(2) != cb.Error(2)  # (&IoError(_), _) => false
+    assert cb.Error(10).variant == "Unsupported" and cb.Error(16).variant == "FormatError"
+
+
+def test_crc_against_oracle_and_vectors():
+    L = _lib.load()
+    for data, exp in KAT["crc8"]["cases"]:
+        assert L.clx_crc8(bytes(data), len(data)) == exp
+    for data, exp in KAT["crc16"]["cases"]:
+        assert L.clx_crc16(bytes(data), len(data)) == exp
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 63, 64, 1000, 6157):
+        buf = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert L.clx_crc16(buf, n) == O.lib().clxo_crc16(buf, n)
+        assert L.clx_crc8(buf, n) == O.lib().clxo_crc8(buf, n)
+
+
+def _hdr_tuple_cb(d):
+    return (d.block_size, d.sample_rate, d.n_channels, d.channel_assignment, d.bits_per_sample, d.flags & 1,
+            d.number, d.header_len)
+
+
+def _hdr_tuple_o(h):
+    return (h.block_size, h.sample_rate, h.n_channels, h.channel_assignment, h.bits_per_sample,
+            h.variable_blocking, h.number, h.header_len)
+
+
+def test_frame_header_parse_matches_oracle_on_mutations():
+    b = synth.generate(synth.SynthConfig(n_frames=6, block_size=1000, n_channels=2, stereo_mode=-1, force_bs16=1,
+                                         variable_blocking=1))
+    rng = np.random.default_rng(5)
+    base = b.data[:16].copy()
+    n_ok = 0
+    for trial in range(4000):
+        buf = base.copy()
+        for _ in range(rng.integers(0, 3)):
+            buf[rng.integers(0, 12)] = rng.integers(0, 256)
+        n = int(rng.integers(0, 17))
+        st_o, h = O.read_frame_header(buf[:n].copy() if n else np.zeros(0, np.uint8))
+        st_c, d = cb.parse_frame_header(buf[:n].copy() if n else np.zeros(0, np.uint8))
+        assert st_o == st_c, (trial, st_o, st_c, buf[:n].tolist())
+        if st_o == 0:
+            n_ok += 1
+            assert _hdr_tuple_cb(d) == _hdr_tuple_o(h)
+    assert n_ok > 50
+
+
+def test_frame_header_all_codes():
+    # every block-size / sample-rate / channel / bps code, CRC fixed up so only the codes decide
+    L = _lib.load()
+    for bs_code in range(16):
+        for sr_code in range(16):
+            for cb_byte in range(0, 256, 1):
+                hdr = bytearray([0xff, 0xf8, (bs_code << 4) | sr_code, cb_byte, 0x05])
+                if bs_code == 6: hdr += b"\x20"
+                if bs_code == 7: hdr += b"\x12\x34"
+                if sr_code == 12: hdr += b"\x2c"
+                if sr_code in (13, 14): hdr += b"\xac\x44"
+                hdr.append(L.clx_crc8(bytes(hdr), len(hdr)))
+                st_o, h = O.read_frame_header(np.frombuffer(bytes(hdr), np.uint8))
+                st_c, d = cb.parse_frame_header(bytes(hdr))
+                assert st_o == st_c, (bs_code, sr_code, cb_byte)
+                if st_o == 0:
+                    assert _hdr_tuple_cb(d) == _hdr_tuple_o(h)
+            if sr_code > 1 and bs_code > 1:
+                break  # the full cross product is only needed for a couple of rows
+
+
+def test_var_length_int_in_header():
+    L = _lib.load()
+    for number in (0, 127, 128, 2047, 2048, 65535, 65536, (1 << 21) - 1, 1 << 21, (1 << 26) - 1, 1 << 26,
+                   (1 << 31) - 1, 1 << 31, (1 << 36) - 1):
+        b = synth.generate(synth.SynthConfig(n_frames=1, block_size=192, n_channels=1, variable_blocking=1))
+        # rebuild the header with our own varint of `number` (sample number: up to 36 bits)
+        def varint(v):
+            if v < 0x80: return bytes([v])
+            extra = 1
+            while extra < 6 and v >= (1 << (6 * extra + 6 - extra)): extra += 1
+            first = (0xff << (7 - extra)) & 0xff | (v >> (6 * extra))
+            return bytes([first]) + bytes(0x80 | ((v >> (6 * i)) & 0x3f) for i in range(extra - 1, -1, -1))
+        hdr = bytearray(b.data[:4].tobytes()) + varint(number)
+        hdr.append(L.clx_crc8(bytes(hdr), len(hdr)))
+        st, d = cb.parse_frame_header(bytes(hdr))
+        st_o, h = O.read_frame_header(np.frombuffer(bytes(hdr), np.uint8))
+        assert st == 0 and st_o == 0 and d.number == number == h.number
+    k = KAT["var_length_int"]  # src/frame.rs:107-129 through the oracle-independent product parser
+    hdr0 = bytes([0xff, 0xf9, 0x19, 0x08])
+    at = 0
+    for exp in k["values"]:
+        st, d = cb.parse_frame_header(hdr0 + bytes(k["bytes"][at:]) + b"\0" * 4, flags=cb.OPT_NO_VERIFY_CRC)
+        assert st == 0 and d.number == exp
+        at += d.header_len - 5
+    assert cb.parse_frame_header(hdr0 + bytes(k["bytes"][at:]), flags=1)[0] == 6
+
+
+def test_open_stream_matches_golden(golden):
+    for name in golden["names"]:
+        name = str(name)
+        meta = golden[f"{name}__meta"]
+        data = golden[f"{name}__bytes"]
+        try:
+            si, first = cb.open_stream(data)
+            st = 0
+        except cb.Error as e:
+            st = e.status
+        assert st == meta[0], name
+        if st == 0:
+            assert first == meta[1] and si.channels == meta[2] and si.bits_per_sample == meta[3]
+            assert (si.samples or 0) == meta[4]
+            assert si.md5sum == bytes(golden[f"{name}__md5"])
+    # reference tests/testsamples.rs:404-426
+    with pytest.raises(cb.Error) as e:
+        cb.open_stream(golden["large_vendor_string__bytes"])
+    assert e.value == cb.Error(43)
+    with pytest.raises(cb.Error) as e:
+        cb.open_stream(golden["large_vorbis_comment_block__bytes"])
+    assert e.value.variant == "Unsupported"
+
+
+@pytest.mark.parametrize("cfgname", ["c2", "c3", "c4", "c5"])
+def test_demux_finds_every_frame(cfgname):
+    n = {"c2": 40, "c3": 40, "c4": 44, "c5": 3}[cfgname]
+    b = synth.workload(cfgname, n)
+    descs, nxt, total, stop = cb.demux_frames(b.data)
+    assert stop == cb.EOF and nxt == b.data.size and descs.size == b.n_frames
+    assert np.array_equal(descs["byte_offset"], b.frame_offsets[:-1])
+    assert np.array_equal(descs["byte_len"], b.frame_lengths)
+    assert (descs["flags"] & cb.FRAME_CRC16_VERIFIED).all()
+    assert (descs["out_offset"] % 4 == 0).all() and total >= b.n_samples
+
+
+def test_demux_false_sync_inside_residual_is_rejected():
+    # plant sync-looking bytes inside frame payloads: the CRC-16 condition must reject them
+    b = synth.workload("c2", 12)
+    data = b.data.copy()
+    hits = 0
+    for i in range(b.n_frames):
+        lo, hi = int(b.frame_offsets[i]) + 16, int(b.frame_offsets[i + 1]) - 4
+        seg = data[lo:hi]
+        idx = np.nonzero((seg[:-1] == 0xff) & ((seg[1:] & 0xfe) == 0xf8))[0]
+        hits += idx.size
+    descs, nxt, total, stop = cb.demux_frames(data)
+    assert descs.size == b.n_frames and np.array_equal(descs["byte_len"], b.frame_lengths)
+    # damaged frame: boundary unknown -> last descriptor is unverified and spans the rest
+    data[int(b.frame_offsets[3]) + 100] ^= 0x10
+    descs, nxt, total, stop = cb.demux_frames(data)
+    assert descs.size >= 3 and not (descs["flags"][-1] & cb.FRAME_CRC16_VERIFIED) or descs.size == b.n_frames
+
+
+def test_block_api_matches_reference_unit_tests():
+    k = KAT["block_sample"]
+    blk = cb.Block(0, k["block_size"], np.array(k["buffer"], dtype=np.int32))
+    assert blk.channels() == k["channels"] and blk.len() == 15 and blk.duration() == 5
+    for ch, i, exp in k["checks"]:
+        assert blk.sample(ch, i) == exp
+    assert blk.channel(1).tolist() == [13, 17, 19, 23, 29]
+    k = KAT["stereo_samples"]
+    blk = cb.Block(0, k["block_size"], np.array(k["buffer"], dtype=np.int32))
+    assert list(blk.stereo_samples()) == [tuple(p) for p in k["pairs"]]
+    with pytest.raises(RuntimeError):
+        cb.Block(0, 5, np.zeros(15, np.int32)).stereo_samples()
+    e = cb.Block.empty()
+    assert e.len() == 0 and e.channels() == 0 and e.time() == 0
+
+
+def test_ensure_buffer_len():
+    # src/frame.rs:639-648: result has exactly new_len elements for every capacity
+    for cap in range(10):
+        for new_len in range(10):
+            buf = np.empty(cap, dtype=np.int32)
+            r = cb._ensure_buffer_len(buf, new_len)
+            assert r.size == new_len
+    big = np.zeros(100, dtype=np.int32)
+    r = cb._ensure_buffer_len(big[:10], 50)
+    assert r.base is big or r.base is big.base or np.shares_memory(r, big)  # capacity reused
+
+
+def test_shard_plan_partitions_and_balances():
+    b = synth.workload("c4", 220)
+    descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
+    for world in (1, 2, 4, 8):
+        plan = shard.plan_shards(descs, world)
+        assert plan[0][0] == 0 and plan[-1][1] == descs.size
+        assert all(plan[i][1] == plan[i + 1][0] for i in range(world - 1))
+        costs = [float(shard.frame_costs(descs[lo:hi]).sum()) for lo, hi in plan]
+        assert max(costs) <= 1.15 * (sum(costs) / world) + float(shard.frame_costs(descs).max())
+        for lo, hi in plan:
+            d, b0, b1, o0, o1 = shard.localize(descs, lo, hi)
+            if d.size:
+                st, hd = cb.parse_frame_header(b.data[b0:b1], int(d["byte_offset"][0]))
+                assert st == 0 and hd.block_size == d["block_size"][0]
