@@ -112,7 +112,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
     if (ctx->device < 0 || ctx->device >= count) { delete ctx; return CLX_ERR_NO_DEVICE; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return CLX_ERR_NO_DEVICE; }
     uint32_t ns = opts && opts->n_streams ? opts->n_streams : 2;
-    ns = std::min<uint32_t>(ns, 64);
+    ns = std::min<uint32_t>(ns, 128);
     ctx->streams.resize(ns);
     for (uint32_t i = 0; i < ns; i++)
         if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
@@ -187,7 +187,8 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         cudaStream_t st = ctx->streams[c];
         const size_t nb = (size_t)(s.b1 - s.b0), nf = s.f1 - s.f0, no = (size_t)(s.o1 - s.o0);
         int rc;
-        if ((rc = grow(ctx, sc.d_bytes, sc.bytes_cap, nb + 64, 4096))) return rc;
+        const size_t nb_pad = ((nb + 63) & ~(size_t)63) + 128;  // whole 64-byte TMA chunks + look-ahead
+        if ((rc = grow(ctx, sc.d_bytes, sc.bytes_cap, nb_pad, 4096))) return rc;
         if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return rc;
         if ((rc = grow(ctx, sc.d_out, sc.out_cap, no + 4, 4096))) return rc;
         if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return rc;
@@ -195,7 +196,7 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs.data() + s.f0, nf * sizeof(clx_frame_desc),
                                 cudaMemcpyHostToDevice, st));
-        CU(ctx, clx::launch_decode(sc.d_bytes, (nb + 3) & ~(size_t)3, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
+        CU(ctx, clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
                                    sc.d_need_hi, st, &ctx->launches));
         CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
@@ -223,11 +224,11 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     }
     clx_batch* b = new clx_batch();
     b->nbytes = nbytes;
-    b->buf_bytes = (nbytes + 3) & ~(size_t)3;
+    b->buf_bytes = ((nbytes + 63) & ~(size_t)63) + 128;  // whole 64-byte TMA chunks + look-ahead
     b->out_elems = out_elems;
     b->n_frames = (uint32_t)n_frames;
-    cudaError_t e = cudaMalloc((void**)&b->d_bytes, b->buf_bytes + 64);
-    if (e == cudaSuccess) e = cudaMemset(b->d_bytes, 0, b->buf_bytes + 64);
+    cudaError_t e = cudaMalloc((void**)&b->d_bytes, b->buf_bytes);
+    if (e == cudaSuccess) e = cudaMemset(b->d_bytes, 0, b->buf_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_descs, std::max<size_t>(1, n_frames) * sizeof(clx_frame_desc));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_out, (out_elems + 4) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));

@@ -39,40 +39,109 @@ constexpr int TILE_WORDS = 32 * 32;  // one 32x32 i32 tile per warp
 enum Mode : int { M_HEADER = 0, M_VERB = 1, M_RICE = 2, M_CONST = 3, M_DONE = 4 };
 
 // ---------------------------------------------------------------------------------
-// Bit cursor: three big-endian 32-bit words of look-ahead + a bit offset into the first.
-// Semantics = claxon's Bitstream (src/input.rs:415-643): MSB-first bit fields.  Words past
-// the end of the byte buffer read as zero; running past the frame's available bytes is
-// detected by position (see `overrun`) and reported as UnexpectedEof.
+// Bit cursor.  Semantics = claxon's Bitstream (src/input.rs:415-643): MSB-first bit fields.
+//
+// Frame bytes are staged from HBM into shared memory by the TMA engine: every lane owns a
+// 128-byte ring (two 64-byte halves) in shared memory and a pair of mbarriers; when its cursor
+// enters a new 64-byte chunk it waits for that chunk's mbarrier and immediately issues a
+// `cp.async.bulk` (16-byte-aligned global source, SASS UBLKCP) for the following chunk, so a
+// chunk is requested ~85 samples (several thousand cycles) before its first word is read and
+// HBM latency never sits on the decode's critical path.  The cursor itself keeps three
+// big-endian words of look-ahead in registers plus one raw word in flight from shared memory.
+// Running past the frame's available bytes is detected by position (see `overrun`) and reported
+// as UnexpectedEof; chunk requests are clamped to the buffer, never faulting.
 // ---------------------------------------------------------------------------------
+constexpr uint32_t RING_LANE_BYTES = 144;  // 2 x 64-byte halves + 16 bytes of bank skew (36 words: 4-way max)
+constexpr uint32_t CHUNK_BYTES = 64;
+
 struct BitCur {
-    const uint32_t* base;  // 4-byte aligned address at or before the frame's first byte
-    uint32_t widx;         // index of the next word to fetch
-    uint32_t wlim;         // first word index that must not be loaded
-    uint32_t cw0, cw1, cw2;
+    const uint8_t* gbase;  // 16-byte aligned global address at or before the frame's first byte
+    uint32_t ring;         // shared-space address of this lane's ring
+    uint32_t bars;         // shared-space address of this lane's two mbarriers
+    uint32_t chunk_lim;    // highest chunk index that lies inside the byte buffer
+    uint32_t widx;         // word index (from gbase) of the next word to load from the ring
+    uint32_t cw0, cw1, cw2, raw;
     uint32_t off;          // 0..31: bits of cw0 already consumed
 };
 
+__device__ __forceinline__ void tma_request_chunk(const BitCur& b, uint32_t c) {
+    const uint32_t bar = b.bars + (c & 1) * 8;
+    const uint32_t dst = b.ring + (c & 1) * CHUNK_BYTES;
+    const uint8_t* src = b.gbase + (size_t)min(c, b.chunk_lim) * CHUNK_BYTES;
+    // order this thread's earlier generic-proxy reads of the half before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CHUNK_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(CHUNK_BYTES), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_wait_chunk(const BitCur& b, uint32_t c) {
+    const uint32_t bar = b.bars + (c & 1) * 8;
+    const uint32_t parity = (c >> 1) & 1;
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ uint32_t ring_load(const BitCur& b, uint32_t w) {
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(b.ring + ((w & 31u) << 2)) : "memory");
+    return x;
+}
 __device__ __forceinline__ uint32_t bc_fetch(BitCur& b) {
-    uint32_t x = 0;
-    if (b.widx < b.wlim) x = __ldg(b.base + b.widx);
+    if ((b.widx & 15u) == 0) {  // first word of a chunk: it must have landed; prefetch the next one
+        const uint32_t c = b.widx >> 4;
+        tma_wait_chunk(b, c);
+        tma_request_chunk(b, c + 1);
+    }
+    uint32_t x = b.raw;
+    b.raw = ring_load(b, b.widx);
     b.widx++;
     return __byte_perm(x, 0, 0x0123);
 }
-__device__ __forceinline__ void bc_init(BitCur& b, const uint8_t* bytes, uint64_t byte_off,
-                                        uint64_t buf_bytes, uint32_t start_bit) {
-    uint64_t aligned = byte_off & ~3ull;
-    b.base = reinterpret_cast<const uint32_t*>(bytes + aligned);
-    uint32_t bit = (uint32_t)(byte_off & 3) * 8 + start_bit;
-    uint64_t words_left = (buf_bytes - aligned + 3) >> 2;
-    b.wlim = words_left > 0xffffffffull ? 0xffffffffu : (uint32_t)words_left;
-    b.widx = bit >> 5;
+// `smem_ring` / `smem_bars`: generic pointers to this lane's ring and mbarrier pair.
+__device__ __forceinline__ void bc_init(BitCur& b, const uint8_t* bytes, uint64_t byte_off, uint64_t buf_bytes,
+                                        uint32_t start_bit, void* smem_ring, void* smem_bars) {
+    const uint64_t aligned = byte_off & ~15ull;
+    b.gbase = bytes + aligned;
+    b.ring = (uint32_t)__cvta_generic_to_shared(smem_ring);
+    b.bars = (uint32_t)__cvta_generic_to_shared(smem_bars);
+    const uint64_t chunks = (buf_bytes - aligned) / CHUNK_BYTES;  // buffer is padded: >= 2
+    b.chunk_lim = (uint32_t)min(chunks - 1, (uint64_t)0x3fffffu);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b.bars) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b.bars + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bit = (uint32_t)(byte_off & 15) * 8 + start_bit;
+    const uint32_t s = bit >> 5;
     b.off = bit & 31;
-    b.cw0 = bc_fetch(b);
-    b.cw1 = bc_fetch(b);
-    b.cw2 = bc_fetch(b);
+    uint32_t c = s >> 4;
+    tma_request_chunk(b, c);
+    tma_wait_chunk(b, c);
+    tma_request_chunk(b, c + 1);
+    uint32_t w[4];
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+        if (i > 0 && ((s + i) & 15u) == 0) {
+            tma_wait_chunk(b, (s + i) >> 4);
+            tma_request_chunk(b, ((s + i) >> 4) + 1);
+        }
+        w[i] = ring_load(b, s + i);
+    }
+    b.cw0 = __byte_perm(w[0], 0, 0x0123);
+    b.cw1 = __byte_perm(w[1], 0, 0x0123);
+    b.cw2 = __byte_perm(w[2], 0, 0x0123);
+    b.raw = w[3];
+    b.widx = s + 4;
 }
-// Bits consumed so far, relative to the aligned base.
-__device__ __forceinline__ uint32_t bc_pos(const BitCur& b) { return (b.widx - 3) * 32 + b.off; }
+// Bits consumed so far, relative to gbase.
+__device__ __forceinline__ uint32_t bc_pos(const BitCur& b) { return (b.widx - 4) * 32 + b.off; }
 __device__ __forceinline__ uint32_t bc_peek(const BitCur& b) { return __funnelshift_l(b.cw1, b.cw0, b.off); }
 __device__ __forceinline__ void bc_skip(BitCur& b, uint32_t n) {  // n <= 32
     b.off += n;
@@ -421,6 +490,8 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                      int* __restrict__ need_hi, int only_flagged) {
     __shared__ __align__(16) int32_t s_tile[WARPS_PER_CTA][TILE_WORDS];
     __shared__ __align__(16) RowInfo s_rows[WARPS_PER_CTA][32];
+    __shared__ __align__(16) uint8_t s_ring[WARPS_PER_CTA][32 * RING_LANE_BYTES];
+    __shared__ __align__(8) uint64_t s_bars[WARPS_PER_CTA][32][2];
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t fidx = blockIdx.x * (WARPS_PER_CTA * 32) + threadIdx.x;
@@ -437,8 +508,6 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     L.order = 0; L.wasted = 0; L.sfbps = 0; L.pred = false; L.is_lpc = false; L.params_done = false;
     L.shift = 0; L.k = 0; L.rem = 0; L.parts_left = 0; L.per = 0; L.pbits = 4; L.cval = 0;
     L.limit_bits = 0; L.frame_bit0 = 0;
-    L.bc.base = reinterpret_cast<const uint32_t*>(bytes);
-    L.bc.widx = 3; L.bc.wlim = 0; L.bc.cw0 = 0; L.bc.cw1 = 0; L.bc.cw2 = 0; L.bc.off = 0;
 #pragma unroll
     for (int j = 0; j < KORD; j++) { L.h[j] = 0; L.c[j] = 0; }
 
@@ -457,8 +526,9 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
         L.bps = d.bits_per_sample;
         L.total = L.bs * L.nch;
         byte_len = d.byte_len;
-        bc_init(L.bc, bytes, d.byte_offset, buf_bytes, (uint32_t)d.header_len * 8);
-        L.frame_bit0 = (uint32_t)(d.byte_offset & 3) * 8;
+        bc_init(L.bc, bytes, d.byte_offset, buf_bytes, (uint32_t)d.header_len * 8,
+                s_ring[warp] + lane * RING_LANE_BYTES, &s_bars[warp][lane][0]);
+        L.frame_bit0 = (uint32_t)(d.byte_offset & 15) * 8;
         L.limit_bits = L.frame_bit0 + byte_len * 8;
         L.mode = M_HEADER;
         ri.out = out + d.out_offset;
@@ -470,6 +540,8 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
             L.mode = M_CONST; L.cval = 0; L.ch = L.nch;
         }
     }
+    if (!have)  // idle lanes follow the same cursor protocol over the start of the buffer (never decoded)
+        bc_init(L.bc, bytes, 0, buf_bytes, 0, s_ring[warp] + lane * RING_LANE_BYTES, &s_bars[warp][lane][0]);
     rows[lane] = ri;
     __syncwarp();
 

@@ -233,7 +233,8 @@ def test_failed_frame_does_not_poison_batch(ctx):
     data = b.data.copy()
     victims = [5, 17, 40]
     for v in victims:
-        data[int(b.frame_offsets[v]) + 9] ^= 0x80  # subframe pad bit -> "invalid subframe header"
+        st, hd = cb.parse_frame_header(data, int(b.frame_offsets[v]))
+        data[int(b.frame_offsets[v]) + hd.header_len] ^= 0x80  # subframe pad bit -> "invalid subframe header"
     descs, out, res = gpu_decode(ctx, data, b.frame_offsets[:-1], b.frame_lengths)
     for i in range(b.n_frames):
         o, n = int(descs[i]["out_offset"]), 8192
