@@ -19,7 +19,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, FRAME_VARIABLE_BLOCKING, FRAME_CRC16_VERIFIED
+from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, FRAME_VARIABLE_BLOCKING,
+                   FRAME_CRC16_VERIFIED)
 
 __all__ = ["Error", "Block", "FrameReader", "FlacReader", "StreamInfo", "Context", "DeviceBatch",
            "parse_frame_header", "demux_frames", "open_stream", "status_str", "DESC_DTYPE", "RESULT_DTYPE"]
@@ -163,9 +164,10 @@ def descs_from_offsets(data, offsets, lengths=None, flags: int = 0) -> tuple[np.
 class Context:
     """clx_ctx: one per host thread / GPU. Raises Error(NO_DEVICE) without a usable GPU."""
 
-    def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2):
+    def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False):
         self._L = _lib.load()
-        opts = _lib.Options(device, 0 if verify_crc else OPT_NO_VERIFY_CRC, n_streams, 0)
+        flags = (0 if verify_crc else OPT_NO_VERIFY_CRC) | (OPT_GENERIC_KERNEL_ONLY if generic_only else 0)
+        opts = _lib.Options(device, flags, n_streams, 0)
         h = C.c_void_p()
         _check(self._L.clx_ctx_create(C.byref(opts), C.byref(h)))
         self._h = h

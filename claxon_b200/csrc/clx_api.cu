@@ -22,6 +22,9 @@ struct clx_ctx {
     std::vector<cudaStream_t> streams;
     std::string last_error;
     uint64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_budget = 227 * 1024;
+    bool use_coop = true;
     // grow-only device scratch for clx_decode_frames, one set per stream (chunk pipelining)
     struct Scratch {
         uint8_t* d_bytes = nullptr; size_t bytes_cap = 0;
@@ -44,6 +47,7 @@ struct clx_batch {
     uint32_t n_frames = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaStream_t last_stream = nullptr;
+    clx::CoopPlan plan;
 };
 
 namespace {
@@ -85,6 +89,19 @@ void verify_crc_range(const uint8_t* bytes, const clx_frame_desc* descs, clx_fra
     }
 }
 
+// Chooses how a set of frames maps onto the cooperative kernel (frames per CTA, shared memory).
+clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t n) {
+    clx::CoopPlan plan;
+    if (!ctx->use_coop) return plan;
+    uint32_t max_elems = 0, max_ch = 0;
+    for (size_t i = 0; i < n; i++) {
+        max_elems = std::max<uint32_t>(max_elems, (uint32_t)descs[i].n_channels * descs[i].block_size);
+        max_ch = std::max<uint32_t>(max_ch, descs[i].n_channels);
+    }
+    clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan);
+    return plan;
+}
+
 void verify_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results,
                 size_t n) {
     if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
@@ -120,6 +137,12 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
             return CLX_ERR_CUDA;
         }
     ctx->scratch.resize(ns);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_budget = prop.sharedMemPerBlockOptin;
+    }
+    if (opts && (opts->flags & CLX_OPT_GENERIC_KERNEL_ONLY)) ctx->use_coop = false;
     ctx->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     *out = ctx;
     return CLX_OK;
@@ -192,12 +215,12 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return rc;
         if ((rc = grow(ctx, sc.d_out, sc.out_cap, no + 4, 4096))) return rc;
         if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return rc;
-        if (!sc.d_need_hi) CU(ctx, cudaMalloc((void**)&sc.d_need_hi, sizeof(int)));
+        if (!sc.d_need_hi) CU(ctx, cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
         CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs.data() + s.f0, nf * sizeof(clx_frame_desc),
                                 cudaMemcpyHostToDevice, st));
         CU(ctx, clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
-                                   sc.d_need_hi, st, &ctx->launches));
+                                   sc.d_need_hi, make_plan(ctx, descs + s.f0, nf), st, &ctx->launches));
         CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
     }
@@ -227,12 +250,13 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     b->buf_bytes = ((nbytes + 63) & ~(size_t)63) + 128;  // whole 64-byte TMA chunks + look-ahead
     b->out_elems = out_elems;
     b->n_frames = (uint32_t)n_frames;
+    b->plan = make_plan(ctx, descs, n_frames);
     cudaError_t e = cudaMalloc((void**)&b->d_bytes, b->buf_bytes);
     if (e == cudaSuccess) e = cudaMemset(b->d_bytes, 0, b->buf_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_descs, std::max<size_t>(1, n_frames) * sizeof(clx_frame_desc));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_out, (out_elems + 4) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_descs, descs, n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
@@ -251,7 +275,7 @@ int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index) {
     b->last_stream = st;
     CU(ctx, cudaEventRecord(b->ev_start, st));
     CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
-                               st, &ctx->launches));
+                               b->plan, st, &ctx->launches));
     CU(ctx, cudaEventRecord(b->ev_stop, st));
     return CLX_OK;
 }
@@ -308,7 +332,7 @@ int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint3
         cudaStream_t st = ctx->streams[i % n_streams];
         b->last_stream = st;
         CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
-                                   b->d_need_hi, st, &ctx->launches));
+                                   b->d_need_hi, b->plan, st, &ctx->launches));
     }
     for (uint32_t s = 1; s < n_streams; s++) {
         CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));

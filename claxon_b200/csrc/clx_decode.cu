@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                      const clx_frame_desc* __restrict__ descs, uint32_t n_frames,
                      int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
-                     int* __restrict__ need_hi, int only_flagged) {
+                     int* __restrict__ need_hi, const int* __restrict__ gate, int select_status) {
     __shared__ __align__(16) int32_t s_tile[WARPS_PER_CTA][TILE_WORDS];
     __shared__ __align__(16) RowInfo s_rows[WARPS_PER_CTA][32];
     __shared__ __align__(16) uint8_t s_ring[WARPS_PER_CTA][32 * RING_LANE_BYTES];
@@ -498,7 +498,9 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     int32_t* tile = s_tile[warp];
     RowInfo* rows = s_rows[warp];
 
-    if (only_flagged && *need_hi == 0) return;
+    // select_status != 0: decode only the frames an earlier kernel marked with that status;
+    // `gate` (if given) is that kernel's "anything marked?" word, so the common case exits at once.
+    if (gate != nullptr && *gate == 0) return;
 
     Lane<KORD> L;
     L.status = CLX_OK;
@@ -512,7 +514,7 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     for (int j = 0; j < KORD; j++) { L.h[j] = 0; L.c[j] = 0; }
 
     bool have = fidx < n_frames;
-    if (have && only_flagged) have = results[fidx].status == CLX_INTERNAL_NEED_HIGH_ORDER;
+    if (have && select_status != 0) have = results[fidx].status == select_status;
     RowInfo ri;
     ri.out = out;
     ri.total = 0;
@@ -686,19 +688,29 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
 // launch
 // ---------------------------------------------------------------------------------
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
-                          uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_need_hi,
-                          cudaStream_t stream, uint64_t* launches) {
+                          uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
+                          const CoopPlan& plan, cudaStream_t stream, uint64_t* launches) {
     if (n_frames == 0) return cudaSuccess;
     const uint32_t per_cta = WARPS_PER_CTA * 32;
     dim3 grid((n_frames + per_cta - 1) / per_cta), block(per_cta);
-    cudaError_t e = cudaMemsetAsync(d_need_hi, 0, sizeof(int), stream);
+    int* d_generic = d_flags;      // set by the cooperative kernel: some frames need the generic kernel
+    int* d_need_hi = d_flags + 1;  // set by the 12-tap generic instance: some frames need 32 taps
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out,
-                                                         d_results, d_need_hi, 0);
-    // Frames with an LPC order above 12 (non-subset streams) were only flagged; the 32-tap
-    // instance picks them up.  It exits immediately when nothing was flagged.
-    decode_frames_kernel<32><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out,
-                                                         d_results, d_need_hi, 1);
+    if (plan.G > 0) {
+        e = launch_coop(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, plan, stream);
+        if (e != cudaSuccess) return e;
+        decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
+                                                             d_need_hi, d_generic, CLX_INTERNAL_NEED_GENERIC);
+        if (launches) *launches += 1;
+    } else {
+        decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
+                                                             d_need_hi, nullptr, 0);
+    }
+    // Frames with an LPC order above 12 (non-subset streams) were only flagged by the 12-tap
+    // instance; the 32-tap instance picks them up.  It exits immediately when nothing was flagged.
+    decode_frames_kernel<32><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
+                                                         d_need_hi, d_need_hi, CLX_INTERNAL_NEED_HIGH_ORDER);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

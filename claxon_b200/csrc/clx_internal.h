@@ -8,13 +8,28 @@
 // Device-only marker: the frame has an LPC order above what the first kernel instance keeps in
 // registers and must be decoded by the 32-tap instance.  Never returned through the C ABI.
 #define CLX_INTERNAL_NEED_HIGH_ORDER (-1)
+// Device-only marker: the cooperative kernel declined the frame (anything irregular: malformed
+// input, escape codes, oversize frames ...); the generic lane-per-frame kernel decodes it.
+#define CLX_INTERNAL_NEED_GENERIC (-2)
 
 namespace clx {
+struct CoopPlan {          // how a batch maps onto the cooperative kernel (G == 0: not at all)
+    uint32_t G = 0;        // frames per CTA (one warp each)
+    uint32_t frame_stride = 0;  // i32 elements of shared memory per frame
+    uint32_t channels = 0;      // channel slots per frame
+    size_t smem_bytes = 0;
+};
+bool coop_plan(uint32_t max_frame_elems, uint32_t max_channels, uint32_t n_frames, int sm_count, size_t smem_budget,
+               CoopPlan* plan);
+cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
+                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, const CoopPlan& plan,
+                        cudaStream_t stream);
 // Decodes `n_frames` frames described by d_descs from d_bytes (256-byte aligned; buf_bytes = allocated
 // size, a multiple of 64 with at least 128 bytes of slack after the last frame) into
 // d_out / d_results on `stream`.  d_need_hi is a 4-byte device scratch word.
+// d_flags: two device ints of scratch.  `plan` (may have G == 0) selects the cooperative fast path.
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
-                          uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_need_hi,
-                          cudaStream_t stream, uint64_t* launches);
+                          uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
+                          const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
 }  // namespace clx
 #endif

@@ -20,9 +20,10 @@ def golden():
     return np.load(path, allow_pickle=False)
 
 
-@pytest.fixture(scope="session")
-def ctx():
+@pytest.fixture(scope="session", params=["coop", "generic"])
+def ctx(request):
+    """Both device paths: the cooperative fast path (with its fallback) and the generic kernel alone."""
     import claxon_b200 as cb
-    c = cb.Context(device=0)
+    c = cb.Context(device=0, generic_only=(request.param == "generic"))
     yield c
     c.close()
