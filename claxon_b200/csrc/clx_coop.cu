@@ -59,14 +59,17 @@ struct Win {
     uint32_t X, Y;
 };
 
+// X holds big-endian (byte-swapped) words ready for bit arithmetic; Y holds them RAW as loaded, so
+// that nothing touches a freshly loaded register until it moves into X a window later.
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 __device__ __forceinline__ uint32_t win_ldg(const Win& w, uint32_t idx) {
     uint32_t v = 0;
     if (idx < w.wlim) v = __ldg(w.base + idx);
-    return __byte_perm(v, 0, 0x0123);
+    return v;
 }
 __device__ __forceinline__ void win_prime(Win& w, uint32_t bitpos, uint32_t lane) {
     w.b0 = bitpos >> 5;
-    w.X = win_ldg(w, w.b0 + lane);
+    w.X = bswap32(win_ldg(w, w.b0 + lane));
     w.Y = win_ldg(w, w.b0 + 32 + lane);
 }
 // Slides the window so that the word containing `bitpos` is X lane 0.
@@ -78,19 +81,17 @@ __device__ __forceinline__ void win_advance(Win& w, uint32_t bitpos, uint32_t la
     const uint32_t xs = __shfl_sync(0xffffffffu, w.X, src);
     const uint32_t ys = __shfl_sync(0xffffffffu, w.Y, src);
     const bool low = lane + d < 32;
-    w.X = low ? xs : ys;
+    w.X = low ? xs : bswap32(ys);
     w.b0 += d;
     uint32_t fresh = 0;
     if (!low) fresh = win_ldg(w, w.b0 + 32 + lane);  // consumed one window later
     w.Y = low ? ys : fresh;
 }
-// 32 bits starting at `bitpos` (uniform across the warp); requires bitpos>>5 in [b0, b0+31].
+// 32 bits starting at `bitpos` (uniform across the warp); requires bitpos>>5 in [b0, b0+30].
 __device__ __forceinline__ uint32_t win_peek32(const Win& w, uint32_t bitpos) {
     const uint32_t i = (bitpos >> 5) - w.b0;
     const uint32_t w0 = __shfl_sync(0xffffffffu, w.X, i & 31);
-    const uint32_t w1x = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);
-    const uint32_t w1y = __shfl_sync(0xffffffffu, w.Y, 0);
-    const uint32_t w1 = (i + 1 < 32) ? w1x : w1y;
+    const uint32_t w1 = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);  // callers keep i <= 30
     return __funnelshift_l(w1, w0, bitpos & 31);
 }
 __device__ __forceinline__ uint32_t top_bits(uint32_t v, uint32_t n) {  // n in [0,32]
@@ -100,9 +101,7 @@ __device__ __forceinline__ uint32_t top_bits(uint32_t v, uint32_t n) {  // n in 
 __device__ __forceinline__ uint32_t win_peek32_lane(const Win& w, uint32_t bitpos) {
     const uint32_t i = (bitpos >> 5) - w.b0;
     const uint32_t w0 = __shfl_sync(0xffffffffu, w.X, i & 31);
-    const uint32_t w1x = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);
-    const uint32_t w1y = __shfl_sync(0xffffffffu, w.Y, 0);
-    const uint32_t w1 = (i + 1 < 32) ? w1x : w1y;
+    const uint32_t w1 = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);  // callers keep i <= 30
     return __funnelshift_l(w1, w0, bitpos & 31);
 }
 __device__ __forceinline__ int32_t sext(uint32_t v, uint32_t bits) {
@@ -137,10 +136,10 @@ __device__ __forceinline__ void walk_word(uint32_t W, uint32_t o, uint32_t k, bo
 // the end of the last decoded code.
 __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint32_t k, uint32_t n_rem, int32_t* out,
                                                 uint32_t lane) {
-    const uint32_t W = w.X;
-    uint32_t WN = __shfl_down_sync(0xffffffffu, w.X, 1);
-    const uint32_t y0 = __shfl_sync(0xffffffffu, w.Y, 0);
-    if (lane == 31) WN = y0;
+    // Lanes 0..30 own one word each (992 bits per window); lane 31 only lends its word as the
+    // right-hand neighbour, so the window never reads Y, whose newest words may still be in flight.
+    const uint32_t W = lane < 31 ? w.X : 0u;
+    const uint32_t WN = __shfl_down_sync(0xffffffffu, w.X, 1);
     const uint32_t s = P - (w.b0 << 5);  // < 32: search offset of lane 0
 
     // speculated chain: every lane assumes its word starts a fresh search
@@ -215,46 +214,97 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
 // ---------------------------------------------------------------------------------
 // Phase 2 helper: the recurrence for one subframe, TAPS taps, in place.
 // ---------------------------------------------------------------------------------
-template <int TAPS>
+// One step of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
+// v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first (they do
+// not depend on this trip's samples), the terms with fresh samples last, most recent last — the
+// serial chain per sample is then one IMAD.WIDE, the shift and the residual add.
+template <int TAPS, int U>
+__device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32_t (&c)[TAPS], const int32_t (&r)[U],
+                                             uint32_t shift) {
+    long long part[U];
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+        long long acc = 0;
+#pragma unroll
+        for (int j = 0; j < TAPS; j++)  // c[j] multiplies v[i + TAPS - 1 - j]; history only here
+            if (i + TAPS - 1 - j < TAPS) acc += (long long)c[j] * (long long)v[i + TAPS - 1 - j];
+        part[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+        long long acc = part[i];
+#pragma unroll
+        for (int j = TAPS - 1; j >= 0; j--)  // fresh samples, oldest first
+            if (i + TAPS - 1 - j >= TAPS) acc += (long long)c[j] * (long long)v[i + TAPS - 1 - j];
+        v[TAPS + i] = (int32_t)(acc >> shift) + r[i];
+    }
+}
+
+// The recurrence for one subframe per lane, in place.  Lanes run in lockstep on t; the bulk of the
+// block is decoded by a predicate-free loop, the ragged head (warm-up, differing orders) and tail
+// (differing block sizes) by a guarded one.
+template <int TAPS, int U>
 __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint32_t order, uint32_t shift,
-                                                const int16_t* coefs, bool active, uint32_t max_bs) {
-    int32_t c[TAPS], h[TAPS];  // c[j] multiplies h[j]; h[0] = most recent sample
+                                                const int16_t* coefs, bool active) {
+    int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
     for (int j = 0; j < TAPS; j++) {
         c[j] = (active && (uint32_t)j < order) ? (int32_t)coefs[j] : 0;
+        // Opaque to the optimiser: otherwise the i16 -> i64 promotion is folded into a full 64-bit
+        // multiply (3 instructions) instead of one signed 32x32+64 IMAD.WIDE per tap.
+        asm volatile("" : "+r"(c[j]));
         h[j] = 0;
     }
-    // lanes of a warp run in lockstep on t; a lane only touches its own subframe
-    int32_t rn[4];  // residuals of the next trip, loaded one trip ahead (shared-memory latency off the chain)
+    const uint32_t max_bs = __reduce_max_sync(0xffffffffu, active ? bs : 0u);
+    const uint32_t min_bs = __reduce_min_sync(0xffffffffu, active ? bs : 0xffffffffu);
+    const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
+    const uint32_t head_end = min(max_bs, (max_order + (uint32_t)U - 1) / (uint32_t)U * (uint32_t)U);
+    const uint32_t bulk_end = head_end + (min_bs > head_end ? (min_bs - head_end) / (uint32_t)U * (uint32_t)U : 0u);
+
+    auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
+        for (uint32_t t = t0; t < t1; t++) {
+            const bool inside = active && t < bs;
+            int32_t val = inside ? buf[t] : 0;
+            if (t >= order) {
+                long long acc = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) rn[i] = (active && (uint32_t)i < bs) ? buf[i] : 0;
-    for (uint32_t t = 0; t < max_bs; t += 4) {
-        int32_t r[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            r[i] = rn[i];
-            rn[i] = (active && t + 4 + i < bs) ? buf[t + 4 + i] : 0;
-        }
-        int32_t s[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            long long acc = 0;
-#pragma unroll
-            for (int j = TAPS - 1; j >= 0; j--) {  // most recent sample last: shortest dependent chain
-                const int32_t hv = (j >= i) ? h[j - i] : s[i - 1 - j];
-                acc += (long long)c[j] * (long long)hv;
+                for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
+                val += (int32_t)(acc >> shift);
+                if (inside) buf[t] = val;
             }
-            const int32_t pred = (int32_t)(acc >> shift);
-            s[i] = (t + i >= order) ? pred + r[i] : r[i];  // warm-up samples pass through
+#pragma unroll
+            for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = val;
+        }
+    };
+    guarded(0, head_end);
+    if (bulk_end > head_end) {
+        int32_t v[TAPS + U];
+#pragma unroll
+        for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
+        int32_t rn[U];  // residuals are fetched one trip ahead: shared-memory latency stays off the chain
+#pragma unroll
+        for (int i = 0; i < U; i++) rn[i] = buf[head_end + i];
+        for (uint32_t t = head_end; t < bulk_end; t += U) {
+            int32_t r[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) r[i] = rn[i];
+            if (t + U < bulk_end) {
+#pragma unroll
+                for (int i = 0; i < U; i++) rn[i] = buf[t + U + i];
+            }
+            predict_trip<TAPS, U>(v, c, r, shift);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < U; i++) buf[t + i] = v[TAPS + i];
+            }
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (active && t + i < bs && t + i >= order) buf[t + i] = s[i];
-#pragma unroll
-        for (int j = TAPS - 1; j >= 4; j--) h[j] = h[j - 4];
-#pragma unroll
-        for (int i = 0; i < 4 && i < TAPS; i++) h[i] = s[3 - i];
+        for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
     }
+    guarded(bulk_end, max_bs);
 }
 
 __device__ __forceinline__ void decor(uint32_t ca, int32_t a, int32_t b, int32_t& o0, int32_t& o1) {
@@ -374,8 +424,10 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                 P += order * precision;
             } else if (lane < 4) {
                 // Pascal rows with alternating sign; coefs[0] multiplies s[t-1]
-                const int32_t rows[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-                sp->coefs[lane] = (int16_t)rows[order][lane];
+                // row `order` of {1}, {2,-1}, {3,-3,1}, {4,-6,4,-1}, packed one nibble-pair per entry
+                const uint32_t packed = order == 1 ? 0x00000001u : order == 2 ? 0x0000ff02u
+                                      : order == 3 ? 0x0001fd03u : order == 4 ? 0xff04fa04u : 0u;
+                sp->coefs[lane] = (int16_t)(int8_t)(packed >> (8 * lane));
             }
             if (lane == 0) { sp->order = (int32_t)order; sp->shift = (int32_t)shift; }
             // ---- residual (src/subframe.rs:236-380) ----
@@ -452,12 +504,15 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                 }
             }
             const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
-            const uint32_t max_bs = __reduce_max_sync(0xffffffffu, active ? bs : 0u);
             if (max_order == 0) continue;
-            if (max_order <= 4) predict_inplace<4>(sbuf, bs, order, shift, coefs, active, max_bs);
-            else if (max_order <= 8) predict_inplace<8>(sbuf, bs, order, shift, coefs, active, max_bs);
-            else if (max_order <= 12) predict_inplace<12>(sbuf, bs, order, shift, coefs, active, max_bs);
-            else predict_inplace<32>(sbuf, bs, order, shift, coefs, active, max_bs);
+            // idle lanes read (never write) some valid buffer so that the bulk loop needs no guards
+            const uint32_t some = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
+            const unsigned long long alias = __shfl_sync(0xffffffffu, (unsigned long long)sbuf, some);
+            if (!active) sbuf = reinterpret_cast<int32_t*>(alias);
+            if (max_order <= 4) predict_inplace<4, 4>(sbuf, bs, order, shift, coefs, active);
+            else if (max_order <= 8) predict_inplace<8, 8>(sbuf, bs, order, shift, coefs, active);
+            else if (max_order <= 12) predict_inplace<12, 4>(sbuf, bs, order, shift, coefs, active);
+            else predict_inplace<32, 4>(sbuf, bs, order, shift, coefs, active);
         }
     }
     __syncthreads();
