@@ -29,6 +29,7 @@
 
 #include "claxon_b200.h"
 #include <algorithm>
+#include <cstdlib>
 
 #include "clx_internal.h"
 
@@ -38,7 +39,8 @@ struct SubParams {   // one per subframe, shared memory
     int32_t order;   // predictor order; 0 = nothing to predict (constant / verbatim / fixed-0)
     int32_t shift;   // qlp shift (0 for fixed predictors)
     int32_t wasted;  // wasted bits per sample
-    int32_t pad;
+    uint32_t narrow; // 0: predicted with the i64 accumulator; else sum|coef| of a subframe predicted with
+                     // the i32 accumulator (phase 3 verifies that this was exact)
     int16_t coefs[32];  // coefs[j] multiplies s[t-1-j]
 };
 
@@ -218,24 +220,24 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
 // v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first (they do
 // not depend on this trip's samples), the terms with fresh samples last, most recent last — the
 // serial chain per sample is then one IMAD.WIDE, the shift and the residual add.
-template <int TAPS, int U>
+template <int TAPS, int U, typename ACC>
 __device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32_t (&c)[TAPS], const int32_t (&r)[U],
                                              uint32_t shift) {
-    long long part[U];
+    ACC part[U];
 #pragma unroll
     for (int i = 0; i < U; i++) {
-        long long acc = 0;
+        ACC acc = 0;
 #pragma unroll
         for (int j = 0; j < TAPS; j++)  // c[j] multiplies v[i + TAPS - 1 - j]; history only here
-            if (i + TAPS - 1 - j < TAPS) acc += (long long)c[j] * (long long)v[i + TAPS - 1 - j];
+            if (i + TAPS - 1 - j < TAPS) acc += (ACC)c[j] * (ACC)v[i + TAPS - 1 - j];
         part[i] = acc;
     }
 #pragma unroll
     for (int i = 0; i < U; i++) {
-        long long acc = part[i];
+        ACC acc = part[i];
 #pragma unroll
         for (int j = TAPS - 1; j >= 0; j--)  // fresh samples, oldest first
-            if (i + TAPS - 1 - j >= TAPS) acc += (long long)c[j] * (long long)v[i + TAPS - 1 - j];
+            if (i + TAPS - 1 - j >= TAPS) acc += (ACC)c[j] * (ACC)v[i + TAPS - 1 - j];
         v[TAPS + i] = (int32_t)(acc >> shift) + r[i];
     }
 }
@@ -243,7 +245,14 @@ __device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32
 // The recurrence for one subframe per lane, in place.  Lanes run in lockstep on t; the bulk of the
 // block is decoded by a predicate-free loop, the ragged head (warm-up, differing orders) and tail
 // (differing block sizes) by a guarded one.
-template <int TAPS, int U>
+//
+// ACC = long long is the reference's arithmetic verbatim (i64 products and sum).  ACC = int is the
+// same recurrence with 32-bit wrapping multiply-adds — 2.3x cheaper on this chip — and yields
+// bit-identical samples whenever no sum of products leaves the i32 range, i.e. whenever
+// sum|coef| * max|sample| < 2^31: the caller picks it only where that is expected, and phase 3
+// re-checks it against the samples actually produced (if it ever fails the frame is re-decoded by
+// the generic kernel, so the output never depends on the shortcut).
+template <int TAPS, int U, typename ACC>
 __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint32_t order, uint32_t shift,
                                                 const int16_t* coefs, bool active) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
@@ -269,7 +278,7 @@ __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint3
                 long long acc = 0;
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
-                val += (int32_t)(acc >> shift);
+                val += sizeof(ACC) == 8 ? (int32_t)(acc >> shift) : (int32_t)((int32_t)acc >> shift);
                 if (inside) buf[t] = val;
             }
 #pragma unroll
@@ -293,7 +302,7 @@ __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint3
 #pragma unroll
                 for (int i = 0; i < U; i++) rn[i] = buf[t + U + i];
             }
-            predict_trip<TAPS, U>(v, c, r, shift);
+            predict_trip<TAPS, U, ACC>(v, c, r, shift);
             if (active) {
 #pragma unroll
                 for (int i = 0; i < U; i++) buf[t + i] = v[TAPS + i];
@@ -327,7 +336,8 @@ __global__ void __launch_bounds__(COOP_MAX_G * 32)
 decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
                           uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
                           int* __restrict__ need_generic, uint32_t G, uint32_t frame_stride /* i32 elements */,
-                          uint32_t CH /* channel slots per frame = max channels in the batch */) {
+                          uint32_t CH /* channel slots per frame = max channels in the batch */,
+                          uint32_t dbg /* timing experiments only: bit1 skip phase 2, bit2 skip phase 3 */) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     int32_t* s_buf = reinterpret_cast<int32_t*>(smem_raw);
     SubParams* s_par = reinterpret_cast<SubParams*>(smem_raw + (size_t)G * frame_stride * 4);
@@ -387,7 +397,7 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
             const uint32_t sfbps = bps - wasted;
             if (sfbps > 30) { ok = false; break; }
             if ((type == 2 || type == 3) && order > bs) { ok = false; break; }
-            if (lane == 0) { sp->order = 0; sp->shift = 0; sp->wasted = (int32_t)wasted; }
+            if (lane == 0) { sp->order = 0; sp->shift = 0; sp->wasted = (int32_t)wasted; sp->narrow = 0; }
             if (type == 0) {  // constant (src/subframe.rs:382-394)
                 const int32_t v = sext(top_bits(win_peek32(w, P), sfbps), sfbps);
                 P += sfbps;
@@ -480,27 +490,38 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     __syncthreads();
 
     // =========================================================================== phase 2
+    if (!(dbg & 2))
     // subframe slot q = frame * CH + channel; lanes of warp w take slots [32w, 32w+32)
     {
         const uint32_t slots = G * CH;
         for (uint32_t q0 = warp * 32; q0 < slots; q0 += blockDim.x) {
             const uint32_t q = q0 + lane;
             const uint32_t f = q / CH, c = q % CH;
-            bool active = false;
-            uint32_t bs = 0, order = 0, shift = 0;
+            bool active = false, narrow_ok = false;
+            uint32_t bs = 0, order = 0, shift = 0, absum = 0;
             const int16_t* coefs = s_par[0].coefs;
+            SubParams* lane_sp = nullptr;
             int32_t* sbuf = s_buf;
             if (q < slots && s_hdr[f].ok) {
                 const uint32_t gf = blockIdx.x * G + f;
                 const uint32_t nch = descs[gf].n_channels;
                 if (c < nch) {
                     bs = descs[gf].block_size;
-                    const SubParams* sp = &s_par[f * CH + c];
+                    SubParams* sp = &s_par[f * CH + c];
+                    lane_sp = sp;
                     order = (uint32_t)sp->order;
                     shift = (uint32_t)sp->shift;
                     coefs = sp->coefs;
                     sbuf = s_buf + (size_t)f * frame_stride + (size_t)c * bs;
                     active = order > 0;
+                    if (active) {
+                        for (uint32_t j = 0; j < order; j++) absum += (uint32_t)abs((int)coefs[j]);
+                        // nominal sample width of this subframe (one extra bit for a side channel)
+                        const uint32_t ca = descs[gf].channel_assignment;
+                        uint32_t bits = descs[gf].bits_per_sample;
+                        if (ca == 9) bits += (c == 0); else if (ca == 8 || ca == 10) bits += (c == 1);
+                        narrow_ok = ((unsigned long long)absum << bits) < (1ull << 31);
+                    }
                 }
             }
             const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
@@ -509,17 +530,27 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
             const uint32_t some = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
             const unsigned long long alias = __shfl_sync(0xffffffffu, (unsigned long long)sbuf, some);
             if (!active) sbuf = reinterpret_cast<int32_t*>(alias);
-            if (max_order <= 4) predict_inplace<4, 4>(sbuf, bs, order, shift, coefs, active);
-            else if (max_order <= 8) predict_inplace<8, 8>(sbuf, bs, order, shift, coefs, active);
-            else if (max_order <= 12) predict_inplace<12, 4>(sbuf, bs, order, shift, coefs, active);
-            else predict_inplace<32, 4>(sbuf, bs, order, shift, coefs, active);
+            // i32 accumulator where sum|coef| * 2^sample_bits leaves headroom in i32 for every lane
+            const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
+            if (active && lane_sp != nullptr) lane_sp->narrow = all_narrow ? absum : 0u;
+            if (all_narrow) {
+                if (max_order <= 4) predict_inplace<4, 4, int>(sbuf, bs, order, shift, coefs, active);
+                else if (max_order <= 8) predict_inplace<8, 8, int>(sbuf, bs, order, shift, coefs, active);
+                else if (max_order <= 12) predict_inplace<12, 4, int>(sbuf, bs, order, shift, coefs, active);
+                else predict_inplace<32, 4, int>(sbuf, bs, order, shift, coefs, active);
+            } else {
+                if (max_order <= 4) predict_inplace<4, 4, long long>(sbuf, bs, order, shift, coefs, active);
+                else if (max_order <= 8) predict_inplace<8, 8, long long>(sbuf, bs, order, shift, coefs, active);
+                else if (max_order <= 12) predict_inplace<12, 4, long long>(sbuf, bs, order, shift, coefs, active);
+                else predict_inplace<32, 4, long long>(sbuf, bs, order, shift, coefs, active);
+            }
         }
     }
     __syncthreads();
 
     // =========================================================================== phase 3
     for (uint32_t f = 0; f < G; f++) {
-        if (!s_hdr[f].ok) continue;
+        if (!s_hdr[f].ok || (dbg & 4)) continue;
         const uint32_t gf = blockIdx.x * G + f;
         const clx_frame_desc d = descs[gf];
         const uint32_t bs = d.block_size, nch = d.n_channels, ca = d.channel_assignment;
@@ -527,6 +558,22 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
         int32_t* o = out + d.out_offset;
         const SubParams* sp = &s_par[f * CH];
         const bool vec = ((bs & 3) == 0) && ((d.out_offset & 3) == 0);
+        // Subframes predicted with the i32 accumulator: exact iff sum|coef| * max|sample| < 2^31.
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t absum = sp[c].narrow;
+            if (absum == 0) continue;  // warp-uniform (shared memory broadcast)
+            uint32_t m = 0;
+            const int32_t* cb = fbuf + (size_t)c * bs;
+            for (uint32_t t = threadIdx.x; t < bs; t += blockDim.x) {
+                const int32_t v = cb[t];
+                m = max(m, (uint32_t)(v < 0 ? 0u - (uint32_t)v : (uint32_t)v));
+            }
+            m = __reduce_max_sync(0xffffffffu, m);
+            if ((unsigned long long)absum * m >= (1ull << 31) && lane == 0) {
+                results[gf].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
+                *need_generic = 1;
+            }
+        }
         if (ca >= 8) {
             const uint32_t w0 = (uint32_t)sp[0].wasted, w1 = (uint32_t)sp[1].wasted;
             if (vec) {
@@ -600,10 +647,11 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    static const uint32_t dbg = getenv("CLX_COOP_DEBUG") ? (uint32_t)atoi(getenv("CLX_COOP_DEBUG")) : 0u;
     dim3 grid((n_frames + plan.G - 1) / plan.G), block(32 * plan.G);
     decode_frames_coop_kernel<<<grid, block, plan.smem_bytes, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out,
                                                                         d_results, d_need_generic, plan.G,
-                                                                        plan.frame_stride, plan.channels);
+                                                                        plan.frame_stride, plan.channels, dbg);
     return cudaGetLastError();
 }
 

@@ -228,6 +228,17 @@ def test_wrapping_arithmetic_parity(ctx):
     assert_batch_equals_oracle(ctx, b)
 
 
+def test_narrow_accumulator_shortcut_is_verified(ctx):
+    """Small coefficients pick the fast path's i32 accumulator; huge (wrapping) samples then violate its
+    exactness condition, which the kernel must notice and hand the frame to the exact path."""
+    cfg = synth.SynthConfig(n_frames=16, block_size=1024, n_channels=2, bps=16, stereo_mode=0, type_mask=8,
+                            lpc_min_order=1, lpc_max_order=8, qlp_precision=5, rice_mode=-2, rice_kmin=26,
+                            rice_kmax=29, rice2=1, residual_mean=2.0e8, max_porder=1)
+    b = synth.generate(cfg)
+    assert np.abs(b.pcm.astype(np.int64)).max() > 2**29
+    assert_batch_equals_oracle(ctx, b)
+
+
 def test_failed_frame_does_not_poison_batch(ctx):
     b = synth.workload("c2", 48)
     data = b.data.copy()
