@@ -46,9 +46,12 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples nvidia-smi clocks / throttle reasons; `stop(t0, t1)` keeps the samples taken inside the
+    timed region [t0, t1] (wall clock), falling back to the nearest ones when the region is shorter than
+    the sampling period."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
@@ -56,40 +59,49 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + 3.0
+            while not self.rows and time.time() < t_end:  # wait for the first sample: nvidia-smi starts slowly
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        parsed = []
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                parsed.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [p for p in parsed if t0 is not None and t0 - 0.02 <= p[0] <= t1 + 0.04]
+        note = "inside timed region"
+        if not inside and parsed:
+            mid = ((t0 or 0) + (t1 or 0)) / 2
+            inside = sorted(parsed, key=lambda p: abs(p[0] - mid))[:3]
+            note = "timed region shorter than the sampling period: nearest samples"
+        sm = [p[1] for p in inside]
+        reasons = sorted({n for p in inside for n in p[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": inside[0][2] if inside else None,
+                "reasons": reasons, "samples": len(sm), "note": note}
 
 
 def measured_peak_gbs():
@@ -130,13 +142,13 @@ def cpu_decode_rate(batch, threads, min_seconds):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="claxon_b200", choices=["claxon_b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--frames", type=int, default=None, help="override frames per batch")
-    ap.add_argument("--inflight", type=int, default=48, help="distinct device-resident batches cycled")
-    ap.add_argument("--streams", type=int, default=16)
+    ap.add_argument("--inflight", type=int, default=16, help="distinct device-resident batches cycled")
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     args = ap.parse_args()
@@ -247,16 +259,17 @@ def main():
     single_ms = float(np.median(single))
 
     # ---- steady state: K steps, several batches in flight
-    launches0 = ctx.launch_count
-    ctx.run_steps(batches, max(args.warmup, 3), args.streams)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    ctx.run_steps(batches, max(args.warmup, 3), args.streams)
+    barrier()
     launches1 = ctx.launch_count
+    t_wall0 = time.time()
     ms = ctx.run_steps(batches, args.steps, args.streams)
+    t_wall1 = time.time()
     gpu_launches = ctx.launch_count - launches1
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall1)
     ms = max_over_ranks(ms)
     value = n_samples * args.steps * world / (ms / 1e3) / 1e6
 

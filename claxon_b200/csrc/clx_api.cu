@@ -35,6 +35,7 @@ struct clx_ctx {
     };
     std::vector<Scratch> scratch;
     std::vector<clx_frame_desc> h_descs;  // rebased descriptors of the chunk in flight
+    std::vector<uint8_t> crc_verdict;     // per frame: CRC-16 of the claimed span matched
     unsigned host_threads = 1;
 };
 
@@ -74,18 +75,48 @@ int grow(clx_ctx* ctx, T*& ptr, size_t& cap, size_t need, size_t slack) {
     return CLX_OK;
 }
 
-// The frame CRC-16 (src/frame.rs:752-763) is checked on the host, after — and only when — the
-// subframes decoded, so subframe errors keep their precedence over "frame CRC mismatch".
-void verify_crc_range(const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results, size_t lo,
-                      size_t hi) {
+// The frame CRC-16 (src/frame.rs:752-763) is checked on the host, and takes effect only when the
+// subframes decoded, so subframe errors keep their precedence over "frame CRC mismatch".  The CRC of
+// the span the descriptor claims (byte_len) is computed while the GPU is busy; after the kernels a
+// frame only needs a second look if it ended somewhere else.
+void precompute_crc_range(const uint8_t* bytes, const clx_frame_desc* descs, uint8_t* verdict, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; i++) {
+        const clx_frame_desc& d = descs[i];
+        if (d.flags & CLX_FRAME_CRC16_VERIFIED) { verdict[i] = 1; continue; }  // demuxer already matched it
+        if (d.byte_len < 2) { verdict[i] = 0; continue; }
+        const uint8_t* f = bytes + d.byte_offset;
+        const uint16_t stored = (uint16_t)(((uint32_t)f[d.byte_len - 2] << 8) | f[d.byte_len - 1]);
+        verdict[i] = clx_crc16(f, d.byte_len - 2) == stored ? 1 : 0;
+    }
+}
+
+void precompute_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, size_t n) {
+    ctx->crc_verdict.assign(n, 0);
+    if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
+    uint8_t* verdict = ctx->crc_verdict.data();
+    unsigned nt = std::min<unsigned>(ctx->host_threads, (unsigned)std::max<size_t>(1, n / 64));
+    if (nt <= 1) return precompute_crc_range(bytes, descs, verdict, 0, n);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++)
+        th.emplace_back(precompute_crc_range, bytes, descs, verdict, n * t / nt, n * (t + 1) / nt);
+    precompute_crc_range(bytes, descs, verdict, 0, n / nt);
+    for (auto& x : th) x.join();
+}
+
+void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results, size_t n) {
+    if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
+    for (size_t i = 0; i < n; i++) {
         if (results[i].status != CLX_OK) continue;
         const clx_frame_desc& d = descs[i];
         const uint32_t consumed = results[i].consumed;
-        if ((d.flags & CLX_FRAME_CRC16_VERIFIED) && consumed == d.byte_len) continue;  // demuxer did it
-        const uint8_t* f = bytes + d.byte_offset;
-        const uint16_t stored = (uint16_t)(((uint32_t)f[consumed - 2] << 8) | f[consumed - 1]);
-        if (clx_crc16(f, consumed - 2) != stored) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
+        bool ok;
+        if (consumed == d.byte_len) ok = ctx->crc_verdict[i] != 0;
+        else {  // the frame ended before the end of the span it was given (boundary was a guess)
+            const uint8_t* f = bytes + d.byte_offset;
+            const uint16_t stored = (uint16_t)(((uint32_t)f[consumed - 2] << 8) | f[consumed - 1]);
+            ok = clx_crc16(f, consumed - 2) == stored;
+        }
+        if (!ok) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
     }
 }
 
@@ -100,18 +131,6 @@ clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t 
     }
     clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan);
     return plan;
-}
-
-void verify_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results,
-                size_t n) {
-    if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
-    unsigned nt = std::min<unsigned>(ctx->host_threads, (unsigned)std::max<size_t>(1, n / 64));
-    if (nt <= 1) return verify_crc_range(bytes, descs, results, 0, n);
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++)
-        th.emplace_back(verify_crc_range, bytes, descs, results, n * t / nt, n * (t + 1) / nt);
-    verify_crc_range(bytes, descs, results, 0, n / nt);
-    for (auto& x : th) x.join();
 }
 
 }  // namespace
@@ -224,8 +243,9 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaMemcpyAsync(results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
     }
+    precompute_crc(ctx, bytes, descs, n_frames);  // host work, overlapped with the copies and kernels above
     for (size_t c = 0; c < n_chunks; c++) CU(ctx, cudaStreamSynchronize(ctx->streams[c]));
-    verify_crc(ctx, bytes, descs, results, n_frames);
+    apply_crc(ctx, bytes, descs, results, n_frames);
     return CLX_OK;
 }
 
