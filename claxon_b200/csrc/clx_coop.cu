@@ -50,172 +50,310 @@ struct GroupHeader {  // per frame of the group, shared memory
 };
 
 // ---------------------------------------------------------------------------------
-// Warp-wide bit window: 64 consecutive big-endian words of the frame in two registers per lane
-// (X = words b0..b0+31, Y = words b0+32..b0+63).  Y is loaded one window ahead of its use, so
-// HBM/L2 latency is off the critical path; all field extraction is shuffle + funnel shift.
+// Warp-wide bit window: 256 consecutive big-endian words of the frame, 16-byte aligned.
+// Lane l holds words 4l..4l+3 of the current 128-word window in X (byte-swapped, ready for bit
+// arithmetic) and the same slice of the NEXT window in Y, raw as loaded: Y is fetched one window
+// ahead with a single coalesced 16-byte load per lane and nothing touches it until it slides into
+// X, so HBM/L2 latency stays off the critical path.  All field extraction is shuffle + funnel shift.
 // ---------------------------------------------------------------------------------
+__device__ unsigned long long g_coop_stats[16];  // debug counters
+constexpr uint32_t WPL = 4;            // words per lane
+constexpr uint32_t WIN_WORDS = 32 * WPL;
+
 struct Win {
-    const uint32_t* base;  // 4-byte aligned global address at or before the frame's first byte
-    uint32_t wlim;         // first word index that lies outside the byte buffer (reads give 0)
-    uint32_t b0;           // word index of X lane 0
-    uint32_t X, Y;
+    const uint4* base;  // 16-byte aligned global address at or before the frame's first byte
+    uint32_t qlim;      // first 16-byte group index that lies outside the byte buffer (reads give 0)
+    uint32_t b0;        // word index (multiple of 4) of X[0] of lane 0
+    uint32_t X[WPL], Y[WPL];
+    uint32_t F[WPL];    // words loaded by the previous slide, not yet merged into Y (pending != 0)
+    uint32_t pending;
 };
 
-// X holds big-endian (byte-swapped) words ready for bit arithmetic; Y holds them RAW as loaded, so
-// that nothing touches a freshly loaded register until it moves into X a window later.
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
-__device__ __forceinline__ uint32_t win_ldg(const Win& w, uint32_t idx) {
-    uint32_t v = 0;
-    if (idx < w.wlim) v = __ldg(w.base + idx);
+__device__ __forceinline__ uint4 win_ldg(const Win& w, uint32_t quad) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (quad < w.qlim) v = __ldg(w.base + quad);
     return v;
 }
 __device__ __forceinline__ void win_prime(Win& w, uint32_t bitpos, uint32_t lane) {
-    w.b0 = bitpos >> 5;
-    w.X = bswap32(win_ldg(w, w.b0 + lane));
-    w.Y = win_ldg(w, w.b0 + 32 + lane);
+    w.b0 = (bitpos >> 5) & ~3u;
+    const uint4 x = win_ldg(w, (w.b0 >> 2) + lane), y = win_ldg(w, (w.b0 >> 2) + 32 + lane);
+    w.X[0] = bswap32(x.x); w.X[1] = bswap32(x.y); w.X[2] = bswap32(x.z); w.X[3] = bswap32(x.w);
+    w.Y[0] = y.x; w.Y[1] = y.y; w.Y[2] = y.z; w.Y[3] = y.w;
+    w.pending = 0;
 }
-// Slides the window so that the word containing `bitpos` is X lane 0.
+// Slides the window so that the 16-byte group containing `bitpos` is lane 0's.
 __device__ __forceinline__ void win_advance(Win& w, uint32_t bitpos, uint32_t lane) {
-    const uint32_t d = (bitpos >> 5) - w.b0;
+    const uint32_t nb0 = (bitpos >> 5) & ~3u;
+    const uint32_t d = (nb0 - w.b0) >> 2;  // lanes to shift by
     if (d == 0) return;
     if (d > 32) { win_prime(w, bitpos, lane); return; }
+    // The words fetched by the previous slide are only now folded into Y: a register written by a
+    // load is not touched until a whole window later, so the load's latency is never waited for.
+    if (w.pending) {
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++) w.Y[j] = w.F[j];
+    }
     const uint32_t src = (lane + d) & 31;
-    const uint32_t xs = __shfl_sync(0xffffffffu, w.X, src);
-    const uint32_t ys = __shfl_sync(0xffffffffu, w.Y, src);
     const bool low = lane + d < 32;
-    w.X = low ? xs : bswap32(ys);
-    w.b0 += d;
-    uint32_t fresh = 0;
-    if (!low) fresh = win_ldg(w, w.b0 + 32 + lane);  // consumed one window later
-    w.Y = low ? ys : fresh;
+    w.b0 = nb0;
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) {
+        const uint32_t xs = __shfl_sync(0xffffffffu, w.X[j], src);
+        const uint32_t ys = __shfl_sync(0xffffffffu, w.Y[j], src);
+        w.X[j] = low ? xs : bswap32(ys);
+        w.Y[j] = ys;  // lanes with !low get their real Y from F at the next slide
+    }
+    w.pending = low ? 0u : 1u;
+    if (!low) {
+        const uint4 fresh = win_ldg(w, (nb0 >> 2) + 32 + lane);
+        w.F[0] = fresh.x; w.F[1] = fresh.y; w.F[2] = fresh.z; w.F[3] = fresh.w;
+    }
 }
-// 32 bits starting at `bitpos` (uniform across the warp); requires bitpos>>5 in [b0, b0+30].
+// Word `i` (0 .. WIN_WORDS-1, uniform across the warp) of the window.
+__device__ __forceinline__ uint32_t win_word(const Win& w, uint32_t i) {
+    const uint32_t j = i & 3;
+    const uint32_t mine = j == 0 ? w.X[0] : j == 1 ? w.X[1] : j == 2 ? w.X[2] : w.X[3];
+    return __shfl_sync(0xffffffffu, mine, (i >> 2) & 31);
+}
+// 32 bits starting at `bitpos` (uniform); requires the word of bitpos to be at most WIN_WORDS-2.
 __device__ __forceinline__ uint32_t win_peek32(const Win& w, uint32_t bitpos) {
     const uint32_t i = (bitpos >> 5) - w.b0;
-    const uint32_t w0 = __shfl_sync(0xffffffffu, w.X, i & 31);
-    const uint32_t w1 = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);  // callers keep i <= 30
-    return __funnelshift_l(w1, w0, bitpos & 31);
+    return __funnelshift_l(win_word(w, i + 1), win_word(w, i), bitpos & 31);
 }
 __device__ __forceinline__ uint32_t top_bits(uint32_t v, uint32_t n) {  // n in [0,32]
     return n >= 32 ? v : __funnelshift_l(v, 0, n);
 }
-// Per-lane variant: lane-specific bit positions inside the window (word index <= b0+30).
+// Per-lane variant: every lane asks for its own bit position inside the window.
 __device__ __forceinline__ uint32_t win_peek32_lane(const Win& w, uint32_t bitpos) {
-    const uint32_t i = (bitpos >> 5) - w.b0;
-    const uint32_t w0 = __shfl_sync(0xffffffffu, w.X, i & 31);
-    const uint32_t w1 = __shfl_sync(0xffffffffu, w.X, (i + 1) & 31);  // callers keep i <= 30
+    const uint32_t i = (bitpos >> 5) - w.b0, i1 = i + 1;
+    uint32_t a[WPL], b[WPL];
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) {
+        a[j] = __shfl_sync(0xffffffffu, w.X[j], (i >> 2) & 31);
+        b[j] = __shfl_sync(0xffffffffu, w.X[j], (i1 >> 2) & 31);
+    }
+    const uint32_t w0 = (i & 3) == 0 ? a[0] : (i & 3) == 1 ? a[1] : (i & 3) == 2 ? a[2] : a[3];
+    const uint32_t w1 = (i1 & 3) == 0 ? b[0] : (i1 & 3) == 1 ? b[1] : (i1 & 3) == 2 ? b[2] : b[3];
     return __funnelshift_l(w1, w0, bitpos & 31);
 }
 __device__ __forceinline__ int32_t sext(uint32_t v, uint32_t bits) {
     return ((int32_t)(v << (32 - bits))) >> (32 - bits);
 }
 
-// Terminators of one word for a search that starts at bit `o`: walks code by code (terminator,
-// then k remainder bits), merging with the speculated chain (tm0, x0) as soon as both hit the
-// same terminator.  Returns the terminator mask and the exit phase (search offset in the next word).
-__device__ __forceinline__ void walk_word(uint32_t W, uint32_t o, uint32_t k, bool merge, uint32_t tm0, uint32_t x0,
-                                          uint32_t& tm, uint32_t& x) {
-    tm = 0;
-    x = 0;
-    for (;;) {
-        const uint32_t m = W & (0xffffffffu >> o);
-        if (m == 0) { x = 0; break; }
-        const uint32_t t = __clz(m);
-        const uint32_t bit = 0x80000000u >> t;
-        if (merge && (tm0 & bit)) {
-            tm |= tm0 & (bit | (bit - 1));
-            x = x0;
-            break;
-        }
-        tm |= bit;
-        o = t + 1 + k;
-        if (o >= 32) { x = o - 32; break; }
+// ---------------------------------------------------------------------------------
+// Rice decode of one window.  Vocabulary: a *search* looks for the next unary terminator (a 1 bit)
+// from some bit offset; after a terminator at t the next search starts at t+1+k.  The *phase* of a
+// 32-bit word is the offset at which the first search inside it starts.  A word walked from phase e
+// yields its terminator mask and its exit phase (the next word's entry phase).
+//
+// Every lane owns WPL consecutive words and walks them simultaneously (independent dependency
+// chains, interleaved by the unrolled loop).  Phases are first speculated — every word assumes its
+// left neighbour exits as it would from phase 0 — and then corrected by a fix-point: a word whose
+// entry phase changed is re-walked, but only until it meets a terminator of its own phase-0 chain,
+// from where both chains coincide.
+// ---------------------------------------------------------------------------------
+#ifdef CLX_COOP_STATS
+#define COOP_STAT(i, v) do { const unsigned long long sv_ = (unsigned long long)(v); if (lane == 0) atomicAdd(&g_coop_stats[i], sv_); } while (0)
+#define COOP_CLOCK() clock64()
+#else
+#define COOP_STAT(i, v) do { (void)(v); } while (0)
+#define COOP_CLOCK() 0ll
+#endif
+
+struct Walk {
+    uint32_t tm[WPL];  // terminator masks (bit 31 = first bit of the word)
+    uint32_t x[WPL];   // exit phases
+};
+
+// select without control flow: the optimiser otherwise turns chains of ?: back into branches, which
+// serialises the WPL interleaved walks of a lane.
+__device__ __forceinline__ uint32_t sel32(bool c, uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
+    return r;
+}
+
+// One code of one word, branch-free (everything is a select, so the WPL words of a lane interleave
+// in the instruction stream and their dependency chains overlap).  `o` = current search offset,
+// 64 once the word is finished.  `stm` = speculated terminator mask to merge with (0: never merge).
+__device__ __forceinline__ void walk_step(uint32_t W, uint32_t k, uint32_t stm, uint32_t sx, uint32_t& o, uint32_t& tm,
+                                          uint32_t& x) {
+    const bool active = o < 32;
+    const uint32_t m = W & __funnelshift_rc(0xffffffffu, 0u, o);  // o >= 32 -> 0
+    const uint32_t t = __clz(m);                                   // 32 when nothing is left
+    const uint32_t bit = __funnelshift_rc(0x80000000u, 0u, t);     // 0 when nothing is left
+    const bool hit = bit != 0;
+    const bool mrg = (stm & bit) != 0;
+    const uint32_t no = t + 1 + k;
+    const bool spill = no >= 32;
+    tm |= sel32(mrg, stm & (bit | (bit - 1)), bit);
+    x = sel32(mrg, sx, sel32(hit, sel32(spill, no - 32, x), sel32(active, 0u, x)));
+    o = sel32(active && hit && !mrg && !spill, no, 64u);
+}
+
+// Walks the words flagged in `todo` from phases e[]; when `merge`, a walk stops at the first
+// terminator shared with the speculated chain.  Results for unflagged words are left untouched.
+__device__ __forceinline__ uint32_t walk_words(const uint32_t (&W)[WPL], const uint32_t (&e)[WPL], uint32_t k, uint32_t todo,
+                                           bool merge, const Walk& spec, Walk& out) {
+    uint32_t trips = 0;
+    uint32_t o[WPL];
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) {
+        const bool go = (todo >> j) & 1u;
+        o[j] = sel32(go, e[j], 64u);
+        out.tm[j] = sel32(go, 0u, out.tm[j]);
+        out.x[j] = sel32(go, 0u, out.x[j]);
     }
+    for (;;) {
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++)
+            walk_step(W[j], k, merge ? spec.tm[j] : 0u, spec.x[j], o[j], out.tm[j], out.x[j]);
+        bool more = false;
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++) more |= o[j] < 32;
+        trips++;
+        if (!__any_sync(0xffffffffu, more)) break;
+    }
+    return trips;
 }
 
 // Decodes up to `n_rem` Rice codes with parameter k starting at bit `P` from the current window
 // into out[0..); returns the number decoded (0 = cannot make progress here) and advances P to
-// the end of the last decoded code.
+// the end of the last decoded code.  The very last word of the window is never owned (it only
+// lends its bits as the right-hand neighbour), so Y is not read here.
 __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint32_t k, uint32_t n_rem, int32_t* out,
                                                 uint32_t lane) {
-    // Lanes 0..30 own one word each (992 bits per window); lane 31 only lends its word as the
-    // right-hand neighbour, so the window never reads Y, whose newest words may still be in flight.
-    const uint32_t W = lane < 31 ? w.X : 0u;
-    const uint32_t WN = __shfl_down_sync(0xffffffffu, w.X, 1);
-    const uint32_t s = P - (w.b0 << 5);  // < 32: search offset of lane 0
+    const uint32_t s = P - (w.b0 << 5);      // < 128: where the first search starts
+    const uint32_t first = s >> 5;           // virtual word that contains it (lane 0)
+    uint32_t W[WPL], WN[WPL];
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) W[j] = w.X[j];
+    const uint32_t right = __shfl_down_sync(0xffffffffu, w.X[0], 1);
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) WN[j] = j + 1 < WPL ? w.X[j + 1] : right;
+    // words that take part: from `first` up to the last-but-one word of the window
+    uint32_t live = (1u << WPL) - 1u;
+    if (lane == 0) live &= ~((1u << first) - 1u);
+    if (lane == 31) live &= ~(1u << (WPL - 1));
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++)
+        if (!(live & (1u << j))) W[j] = 0;  // a dead word has no terminators and exits with phase 0
 
-    // speculated chain: every lane assumes its word starts a fresh search
-    uint32_t tm0, x0;
-    walk_word(W, 0, k, false, 0, 0, tm0, x0);
-    // fix-point on the entry phases
-    uint32_t e = __shfl_up_sync(0xffffffffu, x0, 1);
-    if (lane == 0) e = s;
-    uint32_t tm = tm0, x = x0;
-    bool need = e != 0;
+    long long tc0 = COOP_CLOCK();
+    // 1. speculated chains: phase 0 everywhere
+    Walk spec, cur;
+    const uint32_t zero[WPL] = {0, 0, 0, 0};
+    COOP_STAT(0, 1);
+    COOP_STAT(2, walk_words(W, zero, k, live, false, spec, spec));
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++)
+        if (!(live & (1u << j))) { spec.tm[j] = 0; spec.x[j] = 0; }
+    cur = spec;
+    long long tc1 = COOP_CLOCK(); COOP_STAT(5, tc1 - tc0);
+    // 2. fix-point on the entry phases
+    uint32_t e[WPL] = {0, 0, 0, 0};
     for (;;) {
-        if (need) walk_word(W, e, k, true, tm0, x0, tm, x);
-        uint32_t xe = __shfl_up_sync(0xffffffffu, x, 1);
-        need = lane > 0 && xe != e;
-        if (need) e = xe;
-        if (!__any_sync(0xffffffffu, need)) break;
+        const uint32_t left = __shfl_up_sync(0xffffffffu, cur.x[WPL - 1], 1);
+        uint32_t todo = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++) {
+            uint32_t want = j == 0 ? left : cur.x[j - 1];
+            if (lane == 0 && j <= first) want = j == first ? (s & 31) : 0;
+            if (!(live & (1u << j))) want = 0;
+            if (want != e[j]) { e[j] = want; todo |= 1u << j; }
+        }
+        todo &= live;
+        if (!__any_sync(0xffffffffu, todo != 0)) break;
+        COOP_STAT(1, 1);
+        COOP_STAT(3, walk_words(W, e, k, todo, true, spec, cur));
     }
-    // ranks
-    const uint32_t cnt = __popc(tm);
-    uint32_t incl = cnt;
+    long long tc2 = COOP_CLOCK(); COOP_STAT(6, tc2 - tc1);
+    // 3. ranks
+    uint32_t cnt[WPL], lane_cnt = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) { cnt[j] = __popc(cur.tm[j]); lane_cnt += cnt[j]; }
+    uint32_t incl = lane_cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= (uint32_t)d) incl += v;
     }
-    uint32_t excl = incl - cnt;
     uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t rank[WPL];
+    rank[0] = incl - lane_cnt;
+#pragma unroll
+    for (uint32_t j = 1; j < WPL; j++) rank[j] = rank[j - 1] + cnt[j - 1];
     if (total > n_rem) {  // the partition ends inside this window: keep the first n_rem codes
-        if (excl >= n_rem) tm = 0;
-        else if (incl > n_rem) {
-            uint32_t keep = 0, tmp = tm;
-            for (uint32_t j = 0; j < n_rem - excl; j++) {
-                const uint32_t bit = 0x80000000u >> __clz(tmp);
-                keep |= bit;
-                tmp &= ~bit;
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++) {
+            if (rank[j] >= n_rem) cur.tm[j] = 0;
+            else if (rank[j] + cnt[j] > n_rem) {
+                uint32_t keep = 0, tmp = cur.tm[j];
+                for (uint32_t i = 0; i < n_rem - rank[j]; i++) {
+                    const uint32_t bit = 0x80000000u >> __clz(tmp);
+                    keep |= bit;
+                    tmp &= ~bit;
+                }
+                cur.tm[j] = keep;
             }
-            tm = keep;
         }
         total = n_rem;
     }
     if (total == 0) return 0;
-    // end of the last code at or before each lane (window-relative bit offset)
-    uint32_t lane_end = 0;
-    if (tm) lane_end = (lane << 5) + (32 - __ffs(tm)) + 1 + k;
+    // 4. end of the last code at or before each word (window-relative bit offsets)
+    uint32_t wend[WPL], lane_end = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) {
+        wend[j] = cur.tm[j] ? ((lane * WPL + j) << 5) + (32 - __ffs(cur.tm[j])) + 1 + k : 0;
+        lane_end = max(lane_end, wend[j]);
+    }
     uint32_t endi = lane_end;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, endi, d);
+        const uint32_t v = __shfl_up_sync(0xffffffffu, endi, d);
         if (lane >= (uint32_t)d) endi = max(endi, v);
     }
-    uint32_t start = __shfl_up_sync(0xffffffffu, endi, 1);
-    if (lane == 0) start = s;
-    start = max(start, s);
+    uint32_t before = __shfl_up_sync(0xffffffffu, endi, 1);
+    if (lane == 0) before = 0;
     const uint32_t new_end = __shfl_sync(0xffffffffu, endi, 31);
-    // emit
-    uint32_t idx = excl, rest = tm;
-    while (rest) {
-        const uint32_t t = __clz(rest);
-        rest &= ~(0x80000000u >> t);
-        const uint32_t pos = (lane << 5) + t;
-        const uint32_t q = pos - start;
-        const uint32_t hi = __funnelshift_lc(WN, W, t + 1);
-        const uint32_t r = __funnelshift_l(hi, 0, k);
-        const uint32_t u = (q << k) | r;
-        out[idx++] = (int32_t)((u >> 1) ^ (0u - (u & 1u)));
-        start = pos + 1 + k;
+    uint32_t start[WPL];
+    start[0] = max(before, s);
+#pragma unroll
+    for (uint32_t j = 1; j < WPL; j++) start[j] = max(start[j - 1], wend[j - 1]);
+    long long tc3 = COOP_CLOCK(); COOP_STAT(7, tc3 - tc2);
+    // 5. emit: the WPL words of a lane advance together, one code each per trip (predicated)
+    uint32_t rest[WPL];
+#pragma unroll
+    for (uint32_t j = 0; j < WPL; j++) rest[j] = cur.tm[j];
+    for (;;) {
+        bool more = false;
+#pragma unroll
+        for (uint32_t j = 0; j < WPL; j++) {
+            const bool have = rest[j] != 0;
+            const uint32_t t = __clz(rest[j]) & 31;
+            rest[j] &= ~__funnelshift_rc(0x80000000u, 0u, sel32(have, t, 32u));
+            const uint32_t pos = ((lane * WPL + j) << 5) + t;
+            const uint32_t q = pos - start[j];
+            const uint32_t hi = __funnelshift_lc(WN[j], W[j], t + 1);
+            const uint32_t r = __funnelshift_l(hi, 0, k);
+            const uint32_t u = (q << k) | r;
+            const uint32_t val = (u >> 1) ^ (0u - (u & 1u));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.u32 [%0], %1;\n\t}" ::"l"(out + rank[j]), "r"(val),
+                         "r"((uint32_t)have)
+                         : "memory");
+            rank[j] += (uint32_t)have;
+            start[j] = sel32(have, pos + 1 + k, start[j]);
+            more |= rest[j] != 0;
+        }
+        if (!__any_sync(0xffffffffu, more)) break;
     }
+    COOP_STAT(4, total);
+    COOP_STAT(8, COOP_CLOCK() - tc3);
     P = (w.b0 << 5) + new_end;
     return total;
 }
 
-// ---------------------------------------------------------------------------------
-// Phase 2 helper: the recurrence for one subframe, TAPS taps, in place.
-// ---------------------------------------------------------------------------------
 // One step of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
 // v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first (they do
 // not depend on this trip's samples), the terms with fresh samples last, most recent last — the
@@ -252,8 +390,20 @@ __device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32
 // sum|coef| * max|sample| < 2^31: the caller picks it only where that is expected, and phase 3
 // re-checks it against the samples actually produced (if it ever fails the frame is re-decoded by
 // the generic kernel, so the output never depends on the shortcut).
+// Shared-space accessors (LDS/STS with a 32-bit address).  `volatile` keeps their order among
+// themselves and relative to barriers; no memory clobber, so arithmetic schedules freely around them.
+__device__ __forceinline__ int32_t lds32(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+
+// `sbuf` is the subframe's buffer as a 32-bit shared-space address.
 template <int TAPS, int U, typename ACC>
-__device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint32_t order, uint32_t shift,
+__device__ __forceinline__ void predict_inplace(uint32_t sbuf, uint32_t bs, uint32_t order, uint32_t shift,
                                                 const int16_t* coefs, bool active) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
@@ -273,13 +423,13 @@ __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint3
     auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
         for (uint32_t t = t0; t < t1; t++) {
             const bool inside = active && t < bs;
-            int32_t val = inside ? buf[t] : 0;
+            int32_t val = inside ? lds32(sbuf + 4 * t) : 0;
             if (t >= order) {
                 long long acc = 0;
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
                 val += sizeof(ACC) == 8 ? (int32_t)(acc >> shift) : (int32_t)((int32_t)acc >> shift);
-                if (inside) buf[t] = val;
+                if (inside) sts32(sbuf + 4 * t, val);
             }
 #pragma unroll
             for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
@@ -293,19 +443,19 @@ __device__ __forceinline__ void predict_inplace(int32_t* buf, uint32_t bs, uint3
         for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
         int32_t rn[U];  // residuals are fetched one trip ahead: shared-memory latency stays off the chain
 #pragma unroll
-        for (int i = 0; i < U; i++) rn[i] = buf[head_end + i];
+        for (int i = 0; i < U; i++) rn[i] = lds32(sbuf + 4 * (head_end + i));
         for (uint32_t t = head_end; t < bulk_end; t += U) {
             int32_t r[U];
 #pragma unroll
             for (int i = 0; i < U; i++) r[i] = rn[i];
-            if (t + U < bulk_end) {
+            // prefetch of the next trip (reads up to U samples past the bulk on the last trip: still
+            // inside the subframe buffer or the next one, never used)
 #pragma unroll
-                for (int i = 0; i < U; i++) rn[i] = buf[t + U + i];
-            }
+            for (int i = 0; i < U; i++) rn[i] = lds32(sbuf + 4 * (t + U + i));
             predict_trip<TAPS, U, ACC>(v, c, r, shift);
             if (active) {
 #pragma unroll
-                for (int i = 0; i < U; i++) buf[t + i] = v[TAPS + i];
+                for (int i = 0; i < U; i++) sts32(sbuf + 4 * (t + i), v[TAPS + i]);
             }
 #pragma unroll
             for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
@@ -347,6 +497,7 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
     const uint32_t fidx = blockIdx.x * G + warp;
 
     // =========================================================================== phase 1
+    long long tp0 = COOP_CLOCK();
     {
         bool ok = fidx < n_frames;
         clx_frame_desc d;
@@ -357,14 +508,14 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
         if (ok && ((uint64_t)bs * nch > frame_stride || nch > CH || d.bits_per_sample == 0)) ok = false;
         int32_t* fbuf = s_buf + (size_t)warp * frame_stride;
         Win w;
-        const uint64_t aligned = d.byte_offset & ~3ull;
-        w.base = reinterpret_cast<const uint32_t*>(bytes + aligned);
-        w.wlim = (uint32_t)min((buf_bytes - aligned) >> 2, (uint64_t)0x7fffffffu);
-        const uint32_t bit0 = (uint32_t)(d.byte_offset & 3) * 8;
+        const uint64_t aligned = d.byte_offset & ~15ull;
+        w.base = reinterpret_cast<const uint4*>(bytes + aligned);
+        w.qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x7ffffffu);
+        const uint32_t bit0 = (uint32_t)(d.byte_offset & 15) * 8;
         const uint32_t limit = bit0 + d.byte_len * 8;
         uint32_t P = bit0 + (uint32_t)d.header_len * 8;
         if (ok) win_prime(w, P, lane);
-        else { w.b0 = 0; w.X = 0; w.Y = 0; }
+        else { w.b0 = 0; w.pending = 0; for (uint32_t j = 0; j < WPL; j++) { w.X[j] = 0; w.Y[j] = 0; w.F[j] = 0; } }
 
         for (uint32_t ch = 0; ok && ch < nch; ch++) {
             uint32_t bps = d.bits_per_sample;
@@ -459,7 +610,9 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                 if (k == (1u << pbits) - 1u) { ok = false; break; }  // escape code: Unsupported in the reference
                 uint32_t n_rem = part == 0 ? per - order : per;
                 while (n_rem > 0) {
+                    long long ta = COOP_CLOCK();
                     win_advance(w, P, lane);
+                    COOP_STAT(9, COOP_CLOCK() - ta);
                     const uint32_t got = rice_window(w, P, k, n_rem, sbuf + at, lane);
                     if (got == 0 || P > limit) { ok = false; break; }
                     at += got;
@@ -487,6 +640,7 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
             }
         }
     }
+    COOP_STAT(10, COOP_CLOCK() - tp0);
     __syncthreads();
 
     // =========================================================================== phase 2
@@ -520,7 +674,8 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
                         const uint32_t ca = descs[gf].channel_assignment;
                         uint32_t bits = descs[gf].bits_per_sample;
                         if (ca == 9) bits += (c == 0); else if (ca == 8 || ca == 10) bits += (c == 1);
-                        narrow_ok = ((unsigned long long)absum << bits) < (1ull << 31);
+                        // valid streams keep |sample| <= 2^(bits-1); anything beyond is caught by the phase-3 check
+                        narrow_ok = ((unsigned long long)absum << (bits - 1)) < (1ull << 31);
                     }
                 }
             }
@@ -528,22 +683,27 @@ decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
             if (max_order == 0) continue;
             // idle lanes read (never write) some valid buffer so that the bulk loop needs no guards
             const uint32_t some = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
-            const unsigned long long alias = __shfl_sync(0xffffffffu, (unsigned long long)sbuf, some);
-            if (!active) sbuf = reinterpret_cast<int32_t*>(alias);
+            uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sbuf);
+            const uint32_t alias = __shfl_sync(0xffffffffu, saddr, some);
+            if (!active) saddr = alias;
+            long long tl0 = COOP_CLOCK();
             // i32 accumulator where sum|coef| * 2^sample_bits leaves headroom in i32 for every lane
             const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
             if (active && lane_sp != nullptr) lane_sp->narrow = all_narrow ? absum : 0u;
             if (all_narrow) {
-                if (max_order <= 4) predict_inplace<4, 4, int>(sbuf, bs, order, shift, coefs, active);
-                else if (max_order <= 8) predict_inplace<8, 8, int>(sbuf, bs, order, shift, coefs, active);
-                else if (max_order <= 12) predict_inplace<12, 4, int>(sbuf, bs, order, shift, coefs, active);
-                else predict_inplace<32, 4, int>(sbuf, bs, order, shift, coefs, active);
+                if (max_order <= 4) predict_inplace<4, 4, int>(saddr, bs, order, shift, coefs, active);
+                else if (max_order <= 8) predict_inplace<8, 8, int>(saddr, bs, order, shift, coefs, active);
+                else if (max_order <= 12) predict_inplace<12, 4, int>(saddr, bs, order, shift, coefs, active);
+                else predict_inplace<32, 4, int>(saddr, bs, order, shift, coefs, active);
             } else {
-                if (max_order <= 4) predict_inplace<4, 4, long long>(sbuf, bs, order, shift, coefs, active);
-                else if (max_order <= 8) predict_inplace<8, 8, long long>(sbuf, bs, order, shift, coefs, active);
-                else if (max_order <= 12) predict_inplace<12, 4, long long>(sbuf, bs, order, shift, coefs, active);
-                else predict_inplace<32, 4, long long>(sbuf, bs, order, shift, coefs, active);
+                if (max_order <= 4) predict_inplace<4, 4, long long>(saddr, bs, order, shift, coefs, active);
+                else if (max_order <= 8) predict_inplace<8, 8, long long>(saddr, bs, order, shift, coefs, active);
+                else if (max_order <= 12) predict_inplace<12, 4, long long>(saddr, bs, order, shift, coefs, active);
+                else predict_inplace<32, 4, long long>(saddr, bs, order, shift, coefs, active);
             }
+            COOP_STAT(11, COOP_CLOCK() - tl0);
+            COOP_STAT(12, all_narrow ? 1 : 0);
+            COOP_STAT(13, 1);
         }
     }
     __syncthreads();
@@ -656,3 +816,8 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
 }
 
 }  // namespace clx
+
+extern "C" void clx_debug_coop_stats(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, clx::g_coop_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(clx::g_coop_stats, z, sizeof z); }
+}
