@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,9 +35,13 @@ struct clx_ctx {
         int32_t* d_out = nullptr; size_t out_cap = 0;
         clx_frame_result* d_results = nullptr; size_t results_cap = 0;
         int* d_need_hi = nullptr;
+        uint8_t* d_params = nullptr; size_t params_cap = 0;  // fast path: per-subframe predictor parameters
     };
     std::vector<Scratch> scratch;
-    std::vector<clx_frame_desc> h_descs;  // rebased descriptors of the chunk in flight
+    // pinned staging for the small per-frame tables: pageable memory would make the "async" copies
+    // synchronous and serialise the chunk pipeline
+    clx_frame_desc* h_descs = nullptr; size_t h_descs_cap = 0;   // rebased descriptors (H2D)
+    clx_frame_result* h_results = nullptr; size_t h_results_cap = 0;  // results (D2H)
     std::vector<uint8_t> crc_verdict;     // per frame: CRC-16 of the claimed span matched
     unsigned host_threads = 1;
 };
@@ -45,6 +52,7 @@ struct clx_batch {
     int32_t* d_out = nullptr; size_t out_elems = 0;
     clx_frame_result* d_results = nullptr;
     int* d_need_hi = nullptr;
+    void* d_params = nullptr;
     uint32_t n_frames = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -172,8 +180,11 @@ void clx_ctx_destroy(clx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& s : ctx->scratch) {
         cudaFree(s.d_bytes); cudaFree(s.d_descs); cudaFree(s.d_out); cudaFree(s.d_results); cudaFree(s.d_need_hi);
+        cudaFree(s.d_params);
     }
     for (auto s : ctx->streams) cudaStreamDestroy(s);
+    if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
     delete ctx;
 }
 
@@ -197,6 +208,7 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
             (d.channel_assignment >= 8 && d.n_channels != 2) || d.out_offset + elems > out_elems || (!out && elems))
             return CLX_ERR_INVALID_ARGUMENT;
     }
+    const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     // Chunks of frames are pipelined over the context's streams: H2D of chunk i+1 and D2H of
     // chunk i-1 overlap the kernels of chunk i.  A chunk covers a contiguous byte range and a
     // contiguous output range (descriptors in stream order, as the demuxer emits them).
@@ -205,7 +217,16 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
     for (size_t i = 1; i < n_frames && n_chunks > 1; i++)  // chunking needs stream order on both sides
         if (descs[i].byte_offset < descs[i - 1].byte_offset || descs[i].out_offset < descs[i - 1].out_offset)
             n_chunks = 1;
-    ctx->h_descs.assign(descs, descs + n_frames);
+    if (ctx->h_descs_cap < n_frames) {
+        if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+        if (ctx->h_results) cudaFreeHost(ctx->h_results);
+        ctx->h_descs = nullptr; ctx->h_results = nullptr; ctx->h_descs_cap = ctx->h_results_cap = 0;
+        const size_t cap = n_frames + n_frames / 2 + 1024;
+        CU(ctx, cudaHostAlloc((void**)&ctx->h_descs, cap * sizeof(clx_frame_desc), cudaHostAllocDefault));
+        CU(ctx, cudaHostAlloc((void**)&ctx->h_results, cap * sizeof(clx_frame_result), cudaHostAllocDefault));
+        ctx->h_descs_cap = ctx->h_results_cap = cap;
+    }
+    memcpy(ctx->h_descs, descs, n_frames * sizeof(clx_frame_desc));
     struct Span { size_t f0, f1; uint64_t b0, b1, o0, o1; };
     std::vector<Span> spans;
     for (size_t c = 0; c < n_chunks; c++) {
@@ -236,16 +257,27 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return rc;
         if (!sc.d_need_hi) CU(ctx, cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
         CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs.data() + s.f0, nf * sizeof(clx_frame_desc),
+        CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc),
                                 cudaMemcpyHostToDevice, st));
+        const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf);
+        if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return rc;
         CU(ctx, clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
-                                   sc.d_need_hi, make_plan(ctx, descs + s.f0, nf), st, &ctx->launches));
+                                   sc.d_need_hi, sc.d_params, plan, st, &ctx->launches));
         CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(ctx->h_results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
     }
+    static const bool trace = getenv("CLX_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t1 = trace ? now() : 0;
     precompute_crc(ctx, bytes, descs, n_frames);  // host work, overlapped with the copies and kernels above
+    const double t2 = trace ? now() : 0;
     for (size_t c = 0; c < n_chunks; c++) CU(ctx, cudaStreamSynchronize(ctx->streams[c]));
+    const double t3 = trace ? now() : 0;
+    memcpy(results, ctx->h_results, n_frames * sizeof(clx_frame_result));
     apply_crc(ctx, bytes, descs, results, n_frames);
+    if (trace)
+        fprintf(stderr, "[clx] frames=%zu chunks=%zu submit=%.3f ms crc=%.3f ms wait=%.3f ms apply=%.3f ms\n", n_frames,
+                n_chunks, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return CLX_OK;
 }
 
@@ -277,6 +309,7 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_out, (out_elems + 4) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_params, clx::coop_params_bytes(b->plan, b->n_frames) + 16);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_descs, descs, n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
@@ -295,7 +328,7 @@ int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index) {
     b->last_stream = st;
     CU(ctx, cudaEventRecord(b->ev_start, st));
     CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
-                               b->plan, st, &ctx->launches));
+                               b->d_params, b->plan, st, &ctx->launches));
     CU(ctx, cudaEventRecord(b->ev_stop, st));
     return CLX_OK;
 }
@@ -326,6 +359,7 @@ void clx_batch_destroy(clx_ctx* ctx, clx_batch* b) {
     (void)ctx;
     if (!b) return;
     cudaFree(b->d_bytes); cudaFree(b->d_descs); cudaFree(b->d_out); cudaFree(b->d_results); cudaFree(b->d_need_hi);
+    cudaFree(b->d_params);
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     delete b;
@@ -352,7 +386,7 @@ int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint3
         cudaStream_t st = ctx->streams[i % n_streams];
         b->last_stream = st;
         CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
-                                   b->d_need_hi, b->plan, st, &ctx->launches));
+                                   b->d_need_hi, b->d_params, b->plan, st, &ctx->launches));
     }
     for (uint32_t s = 1; s < n_streams; s++) {
         CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));

@@ -1,29 +1,33 @@
-// clx_coop.cu — warp-cooperative frame decode: the fast path of claxon_b200.
+// clx_coop.cu — the fast path of claxon_b200: warp-cooperative entropy decode + lane-per-subframe
+// prediction, as two kernels working in place on the output buffer.
 //
-// One CTA decodes a group of G frames held entirely in shared memory, in three phases:
-//
-//   1. ENTROPY (one warp per frame).  The warp walks its frame's bitstream — subframe header,
-//      warm-up samples, LPC parameters, residual header, Rice partitions (reference
+//   1. `entropy_frames_kernel` — ONE WARP PER FRAME.  The warp walks its frame's bitstream — subframe
+//      header, warm-up samples, LPC parameters, residual header, Rice partitions (reference
 //      src/subframe.rs:29-91, :236-380, :382-415, :651-701) — and decodes the Rice residuals of a
-//      partition 1024 bits at a time with all 32 lanes: each lane owns one 32-bit word of the
-//      window, finds the unary terminators of its word for the speculated code phase, the
-//      phases are made exact with a shuffle fix-point (a lane's entry phase is the previous
-//      lane's exit phase; chains that meet a terminator of the speculated chain merge with it),
-//      ballot-free popcount + shuffle prefix scans give every code its output rank and the end
-//      of the previous code (hence its quotient), and each lane then emits its codes
-//      (rice_to_signed, src/subframe.rs:157-170) straight into the frame's sample buffer.
-//   2. PREDICTION (one lane per subframe).  predict_fixed / predict_lpc_* (src/subframe.rs:
-//      417-474, :524-614) are strictly serial recurrences — the floor in `>> qlp_shift` makes
-//      them non-associative — so every subframe of the group gets one lane, coefficients and
-//      history register-resident, i64 accumulate, arithmetic shift, truncating cast, in place.
-//   3. OUTPUT (all threads).  Wasted-bits shift (src/subframe.rs:216-225), inter-channel
-//      decorrelation (src/frame.rs:319-389) and coalesced 16-byte stores of the planar Block
-//      layout (src/frame.rs:477-481).
+//      partition 4096 bits at a time with all 32 lanes: every lane owns four 32-bit words of the
+//      window and walks them simultaneously for the *speculated* code phase ("a search for the next
+//      unary terminator starts at bit 0 of every word"); a shuffle fix-point then makes the phases
+//      exact — a word's entry phase is its left neighbour's exit phase, and a re-walk from a
+//      corrected phase stops as soon as it meets a terminator of the speculated chain, from where
+//      both coincide; popcount + shuffle prefix sums rank the codes, a shuffle max-scan gives every
+//      code the end of its predecessor (hence its unary quotient), and each lane emits its codes
+//      (rice_to_signed, src/subframe.rs:157-170) at their final position in the frame's output
+//      block.  Residuals, warm-up, verbatim and constant samples therefore already sit where the PCM
+//      will be; predictor parameters go to a small per-subframe table.
+//   2. `predict_frames_kernel` — ONE LANE PER SUBFRAME.  predict_fixed / predict_lpc_* (src/subframe.rs:
+//      417-474, :524-614) are strictly serial recurrences — the floor in `>> qlp_shift` makes them
+//      non-associative — so the parallel axis is the set of subframes: 32 of them advance per warp
+//      instruction, coefficients and history register-resident, residuals streamed from the output
+//      block with 16-byte loads two trips ahead.  Wasted-bits shift (src/subframe.rs:216-225) and
+//      inter-channel decorrelation (src/frame.rs:319-389, partner channel = neighbouring lane, one
+//      shuffle) happen in registers; samples leave through a swizzled 32x32 shared-memory transpose
+//      as coalesced 16-byte stores, over the residuals they replace (the batch is launched back to
+//      back, so the residuals are normally still in the 126 MB L2 when they are read back).
 //
-// Anything this path does not handle exactly — malformed input of any kind, the Rice escape
-// code, unary runs longer than a window, frames larger than the shared-memory budget — is not
-// guessed at: the frame is flagged and the generic lane-per-frame kernel (clx_decode.cu), which
-// reproduces claxon's error precedence, decodes it afterwards.
+// Anything this path does not handle exactly — malformed input of any kind, the Rice escape code,
+// unary runs longer than a window, more than 8 channels — is not guessed at: the frame is flagged
+// and the generic lane-per-frame kernel (clx_decode.cu), which reproduces claxon's error precedence,
+// decodes it afterwards.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,7 +39,7 @@
 
 namespace clx {
 
-struct SubParams {   // one per subframe, shared memory
+struct SubParams {   // one per subframe (global memory, written by the entropy kernel)
     int32_t order;   // predictor order; 0 = nothing to predict (constant / verbatim / fixed-0)
     int32_t shift;   // qlp shift (0 for fixed predictors)
     int32_t wasted;  // wasted bits per sample
@@ -44,10 +48,6 @@ struct SubParams {   // one per subframe, shared memory
     int16_t coefs[32];  // coefs[j] multiplies s[t-1-j]
 };
 
-struct GroupHeader {  // per frame of the group, shared memory
-    int32_t ok;        // 1 = decoded by this kernel, 0 = flagged for the generic kernel / absent
-    uint32_t consumed; // bytes incl. CRC-16
-};
 
 // ---------------------------------------------------------------------------------
 // Warp-wide bit window: 256 consecutive big-endian words of the frame, 16-byte aligned.
@@ -354,10 +354,190 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
     return total;
 }
 
-// One step of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
-// v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first (they do
-// not depend on this trip's samples), the terms with fresh samples last, most recent last — the
-// serial chain per sample is then one IMAD.WIDE, the shift and the residual add.
+// Inter-channel decorrelation of one (ch0, ch1) pair; wrapping i32 (src/frame.rs:319-389).
+__device__ __forceinline__ void decor(uint32_t ca, int32_t a, int32_t b, int32_t& o0, int32_t& o1) {
+    if (ca == 8) { o0 = a; o1 = (int32_t)((uint32_t)a - (uint32_t)b); }
+    else if (ca == 9) { o0 = (int32_t)((uint32_t)a + (uint32_t)b); o1 = b; }
+    else {  // (mid*2 | side&1) +- side is even, so the reference's `/ 2` equals `>> 1`
+        const uint32_t m = ((uint32_t)a << 1) | ((uint32_t)b & 1u);
+        o0 = ((int32_t)(m + (uint32_t)b)) >> 1;
+        o1 = ((int32_t)(m - (uint32_t)b)) >> 1;
+    }
+}
+
+// Per-lane, branch-free form for the predict kernel: the lane holds one channel's sample `own`, its
+// neighbour's is `other`; masks are all-ones / zero and loop invariant (m_sec: this lane is channel 1;
+// m_ls / m_rs / m_ms: the frame's channel assignment).  Returns this lane's decorrelated sample.
+__device__ __forceinline__ int32_t decor_lane(uint32_t own, uint32_t other, uint32_t m_sec, uint32_t m_ls, uint32_t m_rs,
+                                              uint32_t m_ms) {
+    const uint32_t a = (m_sec & other) | (~m_sec & own);   // channel 0 value
+    const uint32_t b = (m_sec & own) | (~m_sec & other);   // channel 1 value
+    const uint32_t bs = (b ^ m_sec) - m_sec;               // +b for channel 0's result, -b for channel 1's
+    const uint32_t mid = (a << 1) | (b & 1u);
+    const uint32_t ms = (uint32_t)(((int32_t)(mid + bs)) >> 1);   // (m + s) / 2 or (m - s) / 2
+    const uint32_t ls = (m_sec & (a - b)) | (~m_sec & a);          // left stays, right = left - side
+    const uint32_t rs = (m_sec & b) | (~m_sec & (a + b));          // left = side + right, right stays
+    const uint32_t any = m_ls | m_rs | m_ms;
+    return (int32_t)((m_ls & ls) | (m_rs & rs) | (m_ms & ms) | (~any & own));
+}
+
+constexpr int ENT_WARPS = 4;   // entropy kernel: frames (warps) per CTA
+constexpr int PRE_WARPS = 4;   // predict kernel: warps per CTA
+constexpr int COOP_MAX_CH = 8;
+
+// ---------------------------------------------------------------------------------
+// Kernel 1: entropy decode, one warp per frame, output block written in place
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENT_WARPS * 32)
+entropy_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
+                      uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
+                      SubParams* __restrict__ params, uint32_t CH, int* __restrict__ need_generic) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t fidx = blockIdx.x * ENT_WARPS + warp;
+    if (fidx >= n_frames) return;
+    const clx_frame_desc d = descs[fidx];
+    const uint32_t bs = d.block_size, nch = d.n_channels, ca = d.channel_assignment;
+    bool ok = nch <= CH && d.bits_per_sample != 0;
+    int32_t* fbuf = out + d.out_offset;
+    Win w;
+    const uint64_t aligned = d.byte_offset & ~15ull;
+    w.base = reinterpret_cast<const uint4*>(bytes + aligned);
+    w.qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x7ffffffu);
+    const uint32_t bit0 = (uint32_t)(d.byte_offset & 15) * 8;
+    const uint32_t limit = bit0 + d.byte_len * 8;
+    uint32_t P = bit0 + (uint32_t)d.header_len * 8;
+    win_prime(w, P, lane);
+
+    for (uint32_t ch = 0; ok && ch < nch; ch++) {
+        uint32_t bps = d.bits_per_sample;
+        if (ca == 9) bps += (ch == 0);                 // side/right: side first (src/frame.rs:725)
+        else if (ca == 8 || ca == 10) bps += (ch == 1);  // src/frame.rs:717, :736
+        int32_t* sbuf = fbuf + (size_t)ch * bs;
+        SubParams* sp = params + (size_t)fidx * CH + ch;
+        win_advance(w, P, lane);
+        // ---- subframe header (src/subframe.rs:29-91) ----
+        const uint32_t head = win_peek32(w, P) >> 24;
+        P += 8;
+        if (head & 0x80u) { ok = false; break; }
+        const uint32_t code = (head >> 1) & 0x3fu;
+        uint32_t order = 0;
+        int type;
+        if (code == 0) type = 0;
+        else if (code == 1) type = 1;
+        else if ((code & 0x3eu) == 0x02u || (code & 0x3cu) == 0x04u || (code & 0x30u) == 0x10u) { ok = false; break; }
+        else if ((code & 0x38u) == 0x08u) { order = code & 7u; if (order > 4) { ok = false; break; } type = 2; }
+        else { order = (code & 0x1fu) + 1; type = 3; }
+        uint32_t wasted = 0;
+        if (head & 1u) {
+            const uint32_t v = win_peek32(w, P);
+            if (v == 0) { ok = false; break; }  // > 31 wasted bits: an error for the generic kernel to name
+            const uint32_t q = __clz(v);
+            wasted = q + 1;
+            P += q + 1;
+        }
+        if (wasted >= bps) { ok = false; break; }
+        const uint32_t sfbps = bps - wasted;
+        if (sfbps > 30) { ok = false; break; }
+        if ((type == 2 || type == 3) && order > bs) { ok = false; break; }
+        if (lane == 0) { sp->order = 0; sp->shift = 0; sp->wasted = (int32_t)wasted; sp->narrow = 0; }
+        if (type == 0) {  // constant (src/subframe.rs:382-394)
+            const int32_t v = sext(top_bits(win_peek32(w, P), sfbps), sfbps);
+            P += sfbps;
+            for (uint32_t i = lane; i < bs; i += 32) sbuf[i] = v;
+            if (P > limit) { ok = false; break; }
+            continue;
+        }
+        // ---- verbatim samples: the whole subframe, or the warm-up (src/subframe.rs:397-415) ----
+        const uint32_t n_raw = type == 1 ? bs : order;
+        for (uint32_t i0 = 0; i0 < n_raw; i0 += 32) {
+            win_advance(w, P, lane);
+            const uint32_t i = i0 + lane;
+            const uint32_t v = win_peek32_lane(w, P + lane * sfbps);
+            if (i < n_raw) sbuf[i] = sext(top_bits(v, sfbps), sfbps);
+            P += min(32u, n_raw - i0) * sfbps;
+        }
+        if (P > limit) { ok = false; break; }
+        if (type == 1) continue;
+        // ---- predictor parameters (src/subframe.rs:427-431, :669-701) ----
+        win_advance(w, P, lane);
+        uint32_t shift = 0;
+        if (type == 3) {
+            const uint32_t pq = win_peek32(w, P) >> 23;  // 4-bit precision-1, 5-bit signed shift
+            P += 9;
+            const uint32_t prec_m1 = pq >> 5;
+            if (prec_m1 == 15) { ok = false; break; }
+            const uint32_t precision = prec_m1 + 1;
+            const int32_t sh = sext(pq & 31u, 5);
+            if (sh < 0) { ok = false; break; }
+            shift = (uint32_t)sh;
+            const uint32_t v = win_peek32_lane(w, P + lane * precision);
+            if (lane < order) sp->coefs[lane] = (int16_t)sext(top_bits(v, precision), precision);
+            P += order * precision;
+        } else if (lane < 4) {
+            // row `order` of {1}, {2,-1}, {3,-3,1}, {4,-6,4,-1}; coefs[0] multiplies s[t-1]
+            const uint32_t packed = order == 1 ? 0x00000001u : order == 2 ? 0x0000ff02u
+                                  : order == 3 ? 0x0001fd03u : order == 4 ? 0xff04fa04u : 0u;
+            sp->coefs[lane] = (int16_t)(int8_t)(packed >> (8 * lane));
+        }
+        if (lane == 0) { sp->order = (int32_t)order; sp->shift = (int32_t)shift; }
+        // ---- residual (src/subframe.rs:236-380) ----
+        win_advance(w, P, lane);
+        const uint32_t rh = win_peek32(w, P) >> 26;  // 2-bit coding method, 4-bit partition order
+        P += 6;
+        const uint32_t method = rh >> 4, po = rh & 15u;
+        if (method > 1) { ok = false; break; }
+        const uint32_t n_part = 1u << po;
+        if ((bs & ((n_part - 1u) & 0xffffu)) != 0) { ok = false; break; }
+        const uint32_t per = bs >> po;
+        if (order > per) { ok = false; break; }
+        const uint32_t pbits = method == 0 ? 4u : 5u;
+        uint32_t at = order;
+        for (uint32_t part = 0; ok && part < n_part; part++) {
+            win_advance(w, P, lane);
+            const uint32_t k = win_peek32(w, P) >> (32 - pbits);
+            P += pbits;
+            if (k == (1u << pbits) - 1u) { ok = false; break; }  // escape code: Unsupported in the reference
+            uint32_t n_rem = part == 0 ? per - order : per;
+            while (n_rem > 0) {
+                win_advance(w, P, lane);
+                const uint32_t got = rice_window(w, P, k, n_rem, sbuf + at, lane);
+                if (got == 0 || P > limit) { ok = false; break; }
+                at += got;
+                n_rem -= got;
+            }
+        }
+        if (P > limit) ok = false;
+    }
+    // frame footer: pad to the byte boundary, the CRC-16 must be readable (src/frame.rs:744-754)
+    uint32_t consumed = 0;
+    if (ok) {
+        const uint32_t end_byte = (P - bit0 + 7) >> 3;
+        consumed = end_byte + 2;
+        if (P > limit || consumed > d.byte_len) ok = false;
+    }
+    if (lane == 0) {
+        clx_frame_result res;
+        res.status = ok ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
+        res.consumed = consumed;
+        results[fidx] = res;
+        if (!ok) *need_generic = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Kernel 2: prediction + wasted shift + decorrelation, one lane per subframe, in place
+// ---------------------------------------------------------------------------------
+// One trip of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
+// v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first (they do not
+// depend on this trip's samples), the terms with fresh samples last, most recent last — the serial
+// chain per sample is then one multiply-add, the shift and the residual add.
+//
+// ACC = long long is the reference's arithmetic verbatim (i64 products and sum).  ACC = int is the same
+// recurrence with 32-bit wrapping multiply-adds — 2.3x cheaper on this chip — and yields bit-identical
+// samples whenever no sum of products leaves the i32 range, i.e. whenever
+// sum|coef| * max|sample| < 2^31: it is chosen only where a valid stream guarantees that, and the
+// condition is re-checked against the samples actually produced (if it ever fails the frame is
+// re-decoded by the generic kernel, so the output never depends on the shortcut).
 template <int TAPS, int U, typename ACC>
 __device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32_t (&c)[TAPS], const int32_t (&r)[U],
                                              uint32_t shift) {
@@ -380,31 +560,42 @@ __device__ __forceinline__ void predict_trip(int32_t (&v)[TAPS + U], const int32
     }
 }
 
-// The recurrence for one subframe per lane, in place.  Lanes run in lockstep on t; the bulk of the
-// block is decoded by a predicate-free loop, the ragged head (warm-up, differing orders) and tail
-// (differing block sizes) by a guarded one.
-//
-// ACC = long long is the reference's arithmetic verbatim (i64 products and sum).  ACC = int is the
-// same recurrence with 32-bit wrapping multiply-adds — 2.3x cheaper on this chip — and yields
-// bit-identical samples whenever no sum of products leaves the i32 range, i.e. whenever
-// sum|coef| * max|sample| < 2^31: the caller picks it only where that is expected, and phase 3
-// re-checks it against the samples actually produced (if it ever fails the frame is re-decoded by
-// the generic kernel, so the output never depends on the shortcut).
-// Shared-space accessors (LDS/STS with a 32-bit address).  `volatile` keeps their order among
-// themselves and relative to barriers; no memory clobber, so arithmetic schedules freely around them.
-__device__ __forceinline__ int32_t lds32(uint32_t addr) {
-    int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) {
-    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v));
+struct PredRow {       // per lane, shared memory: where the lane's samples go
+    int32_t* out;      // subframe's first output element (nullptr: idle lane)
+    uint32_t bs;       // block size
+    uint32_t vec_ok;   // 16-byte stores allowed
+};
+
+__device__ __forceinline__ uint32_t tile_word(uint32_t row, uint32_t col) {
+    return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
 }
 
-// `sbuf` is the subframe's buffer as a 32-bit shared-space address.
+// Writes the warp's 32x32 tile (steps [g0, g0+32) of every lane's subframe) to global memory.
+__device__ __forceinline__ void flush_rows(const int32_t* tile, const PredRow* rows, uint32_t g0, uint32_t lane) {
+    __syncwarp();
+#pragma unroll 2
+    for (uint32_t pass = 0; pass < 8; pass++) {
+        const uint32_t r = pass * 4 + (lane >> 3), grp = lane & 7;
+        const PredRow pr = rows[r];
+        const uint32_t g = g0 + grp * 4;
+        if (pr.out != nullptr && g < pr.bs) {
+            const int4 v = *reinterpret_cast<const int4*>(tile + r * 32 + ((grp ^ (r & 7)) << 2));
+            if (pr.vec_ok && g + 4 <= pr.bs) *reinterpret_cast<int4*>(pr.out + g) = v;
+            else {
+                pr.out[g] = v.x;
+                if (g + 1 < pr.bs) pr.out[g + 1] = v.y;
+                if (g + 2 < pr.bs) pr.out[g + 2] = v.z;
+                if (g + 3 < pr.bs) pr.out[g + 3] = v.w;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <int TAPS, int U, typename ACC>
-__device__ __forceinline__ void predict_inplace(uint32_t sbuf, uint32_t bs, uint32_t order, uint32_t shift,
-                                                const int16_t* coefs, bool active) {
+__device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, uint32_t bs, uint32_t order, uint32_t shift,
+                                             uint32_t wasted, uint32_t ca, bool second, const int16_t* coefs, bool active,
+                                             int32_t* tile, const PredRow* rows, uint32_t lane, int32_t& smin, int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
     for (int j = 0; j < TAPS; j++) {
@@ -417,23 +608,36 @@ __device__ __forceinline__ void predict_inplace(uint32_t sbuf, uint32_t bs, uint
     const uint32_t max_bs = __reduce_max_sync(0xffffffffu, active ? bs : 0u);
     const uint32_t min_bs = __reduce_min_sync(0xffffffffu, active ? bs : 0xffffffffu);
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
-    const uint32_t head_end = min(max_bs, (max_order + (uint32_t)U - 1) / (uint32_t)U * (uint32_t)U);
-    const uint32_t bulk_end = head_end + (min_bs > head_end ? (min_bs - head_end) / (uint32_t)U * (uint32_t)U : 0u);
+    const bool aligned = __all_sync(0xffffffffu, !active || ((reinterpret_cast<uintptr_t>(src) & 15) == 0));
+    const uint32_t head_end = min(max_bs, (max_order + 31u) & ~31u);  // whole tiles
+    const uint32_t bulk_end = (aligned && min_bs > head_end) ? head_end + ((min_bs - head_end) & ~31u) : head_end;
 
+    // emits one finished sample of every lane: wasted shift, decorrelation with the neighbouring lane,
+    // staging into the transpose tile, flush every 32 steps
+    const uint32_t m_sec = second ? 0xffffffffu : 0u, m_ls = ca == 8 ? 0xffffffffu : 0u,
+                   m_rs = ca == 9 ? 0xffffffffu : 0u, m_ms = ca == 10 ? 0xffffffffu : 0u;
+    auto emit = [&](uint32_t t, int32_t s) {
+        int32_t o = (int32_t)((uint32_t)s << wasted);
+        const int32_t partner = __shfl_xor_sync(0xffffffffu, o, 1);
+        o = decor_lane((uint32_t)o, (uint32_t)partner, m_sec, m_ls, m_rs, m_ms);
+        tile[tile_word(lane, t & 31)] = o;
+        if ((t & 31) == 31) flush_rows(tile, rows, t - 31, lane);
+    };
     auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
         for (uint32_t t = t0; t < t1; t++) {
             const bool inside = active && t < bs;
-            int32_t val = inside ? lds32(sbuf + 4 * t) : 0;
+            int32_t val = inside ? src[t] : 0;
             if (t >= order) {
                 long long acc = 0;
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
                 val += sizeof(ACC) == 8 ? (int32_t)(acc >> shift) : (int32_t)((int32_t)acc >> shift);
-                if (inside) sts32(sbuf + 4 * t, val);
             }
 #pragma unroll
             for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
             h[0] = val;
+            if (inside) { smin = min(smin, val); smax = max(smax, val); }
+            emit(t, val);
         }
     };
     guarded(0, head_end);
@@ -441,22 +645,43 @@ __device__ __forceinline__ void predict_inplace(uint32_t sbuf, uint32_t bs, uint
         int32_t v[TAPS + U];
 #pragma unroll
         for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
-        int32_t rn[U];  // residuals are fetched one trip ahead: shared-memory latency stays off the chain
+        // residuals are fetched as 16-byte vectors two trips ahead (idle lanes read lane-0-ish data:
+        // `src` of an idle lane aliases an active one)
+        constexpr int Q = U / 4;
+        int4 r1[Q], r2[Q];
 #pragma unroll
-        for (int i = 0; i < U; i++) rn[i] = lds32(sbuf + 4 * (head_end + i));
+        for (int q = 0; q < Q; q++) {
+            r1[q] = *reinterpret_cast<const int4*>(src + head_end + 4 * q);
+            r2[q] = *reinterpret_cast<const int4*>(src + min(head_end + U + 4 * q, bulk_end - 4));
+        }
         for (uint32_t t = head_end; t < bulk_end; t += U) {
             int32_t r[U];
 #pragma unroll
-            for (int i = 0; i < U; i++) r[i] = rn[i];
-            // prefetch of the next trip (reads up to U samples past the bulk on the last trip: still
-            // inside the subframe buffer or the next one, never used)
-#pragma unroll
-            for (int i = 0; i < U; i++) rn[i] = lds32(sbuf + 4 * (t + U + i));
-            predict_trip<TAPS, U, ACC>(v, c, r, shift);
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < U; i++) sts32(sbuf + 4 * (t + i), v[TAPS + i]);
+            for (int q = 0; q < Q; q++) {
+                r[4 * q] = r1[q].x; r[4 * q + 1] = r1[q].y; r[4 * q + 2] = r1[q].z; r[4 * q + 3] = r1[q].w;
+                r1[q] = r2[q];
+                r2[q] = *reinterpret_cast<const int4*>(src + min(t + 2 * U + 4 * q, bulk_end - 4));
             }
+            predict_trip<TAPS, U, ACC>(v, c, r, shift);
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                smin = min(smin, v[TAPS + i]);
+                smax = max(smax, v[TAPS + i]);
+            }
+            // wasted shift + decorrelation + staging, 4 samples per 16-byte shared store
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                int32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    o[i] = (int32_t)((uint32_t)v[TAPS + 4 * q + i] << wasted);
+                    const int32_t partner = __shfl_xor_sync(0xffffffffu, o[i], 1);
+                    o[i] = decor_lane((uint32_t)o[i], (uint32_t)partner, m_sec, m_ls, m_rs, m_ms);
+                }
+                const uint32_t col = (t + 4 * q) & 31;
+                *reinterpret_cast<int4*>(tile + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) = make_int4(o[0], o[1], o[2], o[3]);
+            }
+            if (((t + U) & 31) == 0) flush_rows(tile, rows, t + U - 32, lane);
 #pragma unroll
             for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
         }
@@ -464,360 +689,118 @@ __device__ __forceinline__ void predict_inplace(uint32_t sbuf, uint32_t bs, uint
         for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
     }
     guarded(bulk_end, max_bs);
+    if (max_bs & 31) flush_rows(tile, rows, max_bs & ~31u, lane);
 }
 
-__device__ __forceinline__ void decor(uint32_t ca, int32_t a, int32_t b, int32_t& o0, int32_t& o1) {
-    if (ca == 8) { o0 = a; o1 = (int32_t)((uint32_t)a - (uint32_t)b); }
-    else if (ca == 9) { o0 = (int32_t)((uint32_t)a + (uint32_t)b); o1 = b; }
-    else {
-        const uint32_t m = ((uint32_t)a << 1) | ((uint32_t)b & 1u);
-        o0 = ((int32_t)(m + (uint32_t)b)) >> 1;
-        o1 = ((int32_t)(m - (uint32_t)b)) >> 1;
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// The kernel.  blockDim = 32 * G; dynamic shared memory = G * frame_stride * 4 + tables.
-// ---------------------------------------------------------------------------------
-constexpr int COOP_MAX_G = 8;
-constexpr int COOP_MAX_CH = 8;
-
-__global__ void __launch_bounds__(COOP_MAX_G * 32)
-decode_frames_coop_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
-                          uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
-                          int* __restrict__ need_generic, uint32_t G, uint32_t frame_stride /* i32 elements */,
-                          uint32_t CH /* channel slots per frame = max channels in the batch */,
-                          uint32_t dbg /* timing experiments only: bit1 skip phase 2, bit2 skip phase 3 */) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    int32_t* s_buf = reinterpret_cast<int32_t*>(smem_raw);
-    SubParams* s_par = reinterpret_cast<SubParams*>(smem_raw + (size_t)G * frame_stride * 4);
-    GroupHeader* s_hdr = reinterpret_cast<GroupHeader*>(s_par + G * CH);
-
+__global__ void __launch_bounds__(PRE_WARPS * 32)
+predict_frames_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, int32_t* __restrict__ out,
+                      clx_frame_result* __restrict__ results, const SubParams* __restrict__ params, uint32_t CH,
+                      int* __restrict__ need_generic) {
+    __shared__ __align__(16) int32_t s_tile[PRE_WARPS][32 * 32];
+    __shared__ __align__(16) PredRow s_rows[PRE_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t fidx = blockIdx.x * G + warp;
+    const uint32_t slot = (blockIdx.x * PRE_WARPS + warp) * 32 + lane;  // CH is a power of two: frames never split
+    const uint32_t f = slot / CH, c = slot % CH;
+    int32_t* tile = s_tile[warp];
+    PredRow* rows = s_rows[warp];
 
-    // =========================================================================== phase 1
-    long long tp0 = COOP_CLOCK();
-    {
-        bool ok = fidx < n_frames;
-        clx_frame_desc d;
-        if (ok) d = descs[fidx];
-        else { d.block_size = 0; d.n_channels = 0; d.bits_per_sample = 0; d.channel_assignment = 0; d.byte_len = 0;
-               d.byte_offset = 0; d.header_len = 0; d.out_offset = 0; }
-        const uint32_t bs = d.block_size, nch = d.n_channels, ca = d.channel_assignment;
-        if (ok && ((uint64_t)bs * nch > frame_stride || nch > CH || d.bits_per_sample == 0)) ok = false;
-        int32_t* fbuf = s_buf + (size_t)warp * frame_stride;
-        Win w;
-        const uint64_t aligned = d.byte_offset & ~15ull;
-        w.base = reinterpret_cast<const uint4*>(bytes + aligned);
-        w.qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x7ffffffu);
-        const uint32_t bit0 = (uint32_t)(d.byte_offset & 15) * 8;
-        const uint32_t limit = bit0 + d.byte_len * 8;
-        uint32_t P = bit0 + (uint32_t)d.header_len * 8;
-        if (ok) win_prime(w, P, lane);
-        else { w.b0 = 0; w.pending = 0; for (uint32_t j = 0; j < WPL; j++) { w.X[j] = 0; w.Y[j] = 0; w.F[j] = 0; } }
-
-        for (uint32_t ch = 0; ok && ch < nch; ch++) {
-            uint32_t bps = d.bits_per_sample;
-            if (ca == 9) bps += (ch == 0);
-            else if (ca == 8 || ca == 10) bps += (ch == 1);
-            int32_t* sbuf = fbuf + (size_t)ch * bs;
-            SubParams* sp = &s_par[warp * CH + ch];
-            win_advance(w, P, lane);
-            // ---- subframe header (src/subframe.rs:29-91) ----
-            uint32_t head = win_peek32(w, P) >> 24;
-            P += 8;
-            if (head & 0x80u) { ok = false; break; }
-            const uint32_t code = (head >> 1) & 0x3fu;
-            uint32_t order = 0;
-            int type;
-            if (code == 0) type = 0;
-            else if (code == 1) type = 1;
-            else if ((code & 0x3eu) == 0x02u || (code & 0x3cu) == 0x04u || (code & 0x30u) == 0x10u) { ok = false; break; }
-            else if ((code & 0x38u) == 0x08u) { order = code & 7u; if (order > 4) { ok = false; break; } type = 2; }
-            else { order = (code & 0x1fu) + 1; type = 3; }
-            uint32_t wasted = 0;
-            if (head & 1u) {
-                const uint32_t v = win_peek32(w, P);
-                if (v == 0) { ok = false; break; }  // > 31 wasted bits: an error for the generic kernel to name
-                const uint32_t q = __clz(v);
-                wasted = q + 1;
-                P += q + 1;
-            }
-            if (wasted >= bps) { ok = false; break; }
-            const uint32_t sfbps = bps - wasted;
-            if (sfbps > 30) { ok = false; break; }
-            if ((type == 2 || type == 3) && order > bs) { ok = false; break; }
-            if (lane == 0) { sp->order = 0; sp->shift = 0; sp->wasted = (int32_t)wasted; sp->narrow = 0; }
-            if (type == 0) {  // constant (src/subframe.rs:382-394)
-                const int32_t v = sext(top_bits(win_peek32(w, P), sfbps), sfbps);
-                P += sfbps;
-                for (uint32_t i = lane; i < bs; i += 32) sbuf[i] = v;
-                if (P > limit) { ok = false; break; }
-                continue;
-            }
-            // ---- verbatim samples: the whole subframe, or the warm-up (src/subframe.rs:397-415) ----
-            const uint32_t n_raw = type == 1 ? bs : order;
-            for (uint32_t i0 = 0; i0 < n_raw; i0 += 32) {
-                win_advance(w, P, lane);
-                const uint32_t i = i0 + lane;
-                const uint32_t pos = P + lane * sfbps;
-                const uint32_t v = win_peek32_lane(w, pos);
-                if (i < n_raw) sbuf[i] = sext(top_bits(v, sfbps), sfbps);
-                P += min(32u, n_raw - i0) * sfbps;
-            }
-            if (P > limit) { ok = false; break; }
-            if (type == 1) continue;
-            // ---- predictor parameters (src/subframe.rs:427-431, :669-701) ----
-            win_advance(w, P, lane);
-            uint32_t shift = 0;
-            if (type == 3) {
-                const uint32_t pq = win_peek32(w, P) >> 23;
-                P += 9;
-                const uint32_t prec_m1 = pq >> 5;
-                if (prec_m1 == 15) { ok = false; break; }
-                const uint32_t precision = prec_m1 + 1;
-                const int32_t sh = sext(pq & 31u, 5);
-                if (sh < 0) { ok = false; break; }
-                shift = (uint32_t)sh;
-                const uint32_t v = win_peek32_lane(w, P + lane * precision);
-                if (lane < order) sp->coefs[lane] = (int16_t)sext(top_bits(v, precision), precision);
-                P += order * precision;
-            } else if (lane < 4) {
-                // Pascal rows with alternating sign; coefs[0] multiplies s[t-1]
-                // row `order` of {1}, {2,-1}, {3,-3,1}, {4,-6,4,-1}, packed one nibble-pair per entry
-                const uint32_t packed = order == 1 ? 0x00000001u : order == 2 ? 0x0000ff02u
-                                      : order == 3 ? 0x0001fd03u : order == 4 ? 0xff04fa04u : 0u;
-                sp->coefs[lane] = (int16_t)(int8_t)(packed >> (8 * lane));
-            }
-            if (lane == 0) { sp->order = (int32_t)order; sp->shift = (int32_t)shift; }
-            // ---- residual (src/subframe.rs:236-380) ----
-            win_advance(w, P, lane);
-            const uint32_t rh = win_peek32(w, P) >> 26;
-            P += 6;
-            const uint32_t method = rh >> 4, po = rh & 15u;
-            if (method > 1) { ok = false; break; }
-            const uint32_t n_part = 1u << po;
-            if ((bs & ((n_part - 1u) & 0xffffu)) != 0) { ok = false; break; }
-            const uint32_t per = bs >> po;
-            if (order > per) { ok = false; break; }
-            const uint32_t pbits = method == 0 ? 4u : 5u;
-            uint32_t at = order;
-            for (uint32_t part = 0; ok && part < n_part; part++) {
-                win_advance(w, P, lane);
-                const uint32_t k = win_peek32(w, P) >> (32 - pbits);
-                P += pbits;
-                if (k == (1u << pbits) - 1u) { ok = false; break; }  // escape code: Unsupported in the reference
-                uint32_t n_rem = part == 0 ? per - order : per;
-                while (n_rem > 0) {
-                    long long ta = COOP_CLOCK();
-                    win_advance(w, P, lane);
-                    COOP_STAT(9, COOP_CLOCK() - ta);
-                    const uint32_t got = rice_window(w, P, k, n_rem, sbuf + at, lane);
-                    if (got == 0 || P > limit) { ok = false; break; }
-                    at += got;
-                    n_rem -= got;
-                }
-            }
-            if (P > limit) ok = false;
-        }
-        // frame footer: pad to the byte boundary, the CRC-16 must be readable (src/frame.rs:744-754)
-        uint32_t consumed = 0;
-        if (ok) {
-            const uint32_t end_byte = (P - bit0 + 7) >> 3;
-            consumed = end_byte + 2;
-            if (P > limit || consumed > d.byte_len) ok = false;
-        }
-        if (lane == 0) {
-            s_hdr[warp].ok = ok ? 1 : 0;
-            s_hdr[warp].consumed = consumed;
-            if (fidx < n_frames) {
-                clx_frame_result res;
-                res.status = ok ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
-                res.consumed = consumed;
-                results[fidx] = res;
-                if (!ok) *need_generic = 1;
-            }
+    bool active = false, narrow_ok = true, second = false;
+    uint32_t bs = 0, order = 0, shift = 0, wasted = 0, ca = 0, absum = 0;
+    const int16_t* coefs = params[0].coefs;
+    int32_t* sub = out;
+    if (f < n_frames && results[f].status == CLX_OK) {
+        const clx_frame_desc d = descs[f];
+        if (c < d.n_channels) {
+            const SubParams* sp = params + (size_t)f * CH + c;
+            active = true;
+            bs = d.block_size;
+            order = (uint32_t)sp->order;
+            shift = (uint32_t)sp->shift;
+            wasted = (uint32_t)sp->wasted;
+            coefs = sp->coefs;
+            ca = d.channel_assignment >= 8 ? d.channel_assignment : 0u;
+            second = c == 1;
+            sub = out + d.out_offset + (size_t)c * bs;
+            for (uint32_t j = 0; j < order; j++) absum += (uint32_t)abs((int)coefs[j]);
+            uint32_t bits = d.bits_per_sample;  // nominal sample width (one extra bit for a side channel)
+            if (d.channel_assignment == 9) bits += (c == 0);
+            else if (d.channel_assignment == 8 || d.channel_assignment == 10) bits += (c == 1);
+            // valid streams keep |sample| <= 2^(bits-1); anything beyond is caught by the check below
+            narrow_ok = ((unsigned long long)absum << (bits - 1)) < (1ull << 31);
         }
     }
-    COOP_STAT(10, COOP_CLOCK() - tp0);
-    __syncthreads();
+    PredRow pr;
+    pr.out = active ? sub : nullptr;
+    pr.bs = bs;
+    pr.vec_ok = ((reinterpret_cast<uintptr_t>(sub) & 15) == 0) ? 1u : 0u;
+    rows[lane] = pr;
+    if (!__any_sync(0xffffffffu, active)) return;
+    // idle lanes read (never write) the residuals of some active lane so that the bulk loop needs no guards
+    const uint32_t some = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
+    const unsigned long long alias = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)sub, some);
+    const int32_t* src = active ? sub : reinterpret_cast<const int32_t*>((uintptr_t)alias);
+    __syncwarp();
 
-    // =========================================================================== phase 2
-    if (!(dbg & 2))
-    // subframe slot q = frame * CH + channel; lanes of warp w take slots [32w, 32w+32)
-    {
-        const uint32_t slots = G * CH;
-        for (uint32_t q0 = warp * 32; q0 < slots; q0 += blockDim.x) {
-            const uint32_t q = q0 + lane;
-            const uint32_t f = q / CH, c = q % CH;
-            bool active = false, narrow_ok = false;
-            uint32_t bs = 0, order = 0, shift = 0, absum = 0;
-            const int16_t* coefs = s_par[0].coefs;
-            SubParams* lane_sp = nullptr;
-            int32_t* sbuf = s_buf;
-            if (q < slots && s_hdr[f].ok) {
-                const uint32_t gf = blockIdx.x * G + f;
-                const uint32_t nch = descs[gf].n_channels;
-                if (c < nch) {
-                    bs = descs[gf].block_size;
-                    SubParams* sp = &s_par[f * CH + c];
-                    lane_sp = sp;
-                    order = (uint32_t)sp->order;
-                    shift = (uint32_t)sp->shift;
-                    coefs = sp->coefs;
-                    sbuf = s_buf + (size_t)f * frame_stride + (size_t)c * bs;
-                    active = order > 0;
-                    if (active) {
-                        for (uint32_t j = 0; j < order; j++) absum += (uint32_t)abs((int)coefs[j]);
-                        // nominal sample width of this subframe (one extra bit for a side channel)
-                        const uint32_t ca = descs[gf].channel_assignment;
-                        uint32_t bits = descs[gf].bits_per_sample;
-                        if (ca == 9) bits += (c == 0); else if (ca == 8 || ca == 10) bits += (c == 1);
-                        // valid streams keep |sample| <= 2^(bits-1); anything beyond is caught by the phase-3 check
-                        narrow_ok = ((unsigned long long)absum << (bits - 1)) < (1ull << 31);
-                    }
-                }
-            }
-            const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
-            if (max_order == 0) continue;
-            // idle lanes read (never write) some valid buffer so that the bulk loop needs no guards
-            const uint32_t some = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
-            uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sbuf);
-            const uint32_t alias = __shfl_sync(0xffffffffu, saddr, some);
-            if (!active) saddr = alias;
-            long long tl0 = COOP_CLOCK();
-            // i32 accumulator where sum|coef| * 2^sample_bits leaves headroom in i32 for every lane
-            const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
-            if (active && lane_sp != nullptr) lane_sp->narrow = all_narrow ? absum : 0u;
-            if (all_narrow) {
-                if (max_order <= 4) predict_inplace<4, 4, int>(saddr, bs, order, shift, coefs, active);
-                else if (max_order <= 8) predict_inplace<8, 8, int>(saddr, bs, order, shift, coefs, active);
-                else if (max_order <= 12) predict_inplace<12, 4, int>(saddr, bs, order, shift, coefs, active);
-                else predict_inplace<32, 4, int>(saddr, bs, order, shift, coefs, active);
-            } else {
-                if (max_order <= 4) predict_inplace<4, 4, long long>(saddr, bs, order, shift, coefs, active);
-                else if (max_order <= 8) predict_inplace<8, 8, long long>(saddr, bs, order, shift, coefs, active);
-                else if (max_order <= 12) predict_inplace<12, 4, long long>(saddr, bs, order, shift, coefs, active);
-                else predict_inplace<32, 4, long long>(saddr, bs, order, shift, coefs, active);
-            }
-            COOP_STAT(11, COOP_CLOCK() - tl0);
-            COOP_STAT(12, all_narrow ? 1 : 0);
-            COOP_STAT(13, 1);
+    const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
+    const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
+    int32_t smin = 0, smax = 0;
+    if (all_narrow) {
+        if (max_order <= 4) predict_rows<4, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else if (max_order <= 8) predict_rows<8, 8, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else if (max_order <= 12) predict_rows<12, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else predict_rows<32, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        // exactness of the i32 accumulator: sum|coef| * max|sample| < 2^31 over the samples produced
+        const uint32_t m = max((uint32_t)smax, 0u - (uint32_t)smin);
+        if (active && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) {
+            results[f].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
+            *need_generic = 1;
         }
-    }
-    __syncthreads();
-
-    // =========================================================================== phase 3
-    for (uint32_t f = 0; f < G; f++) {
-        if (!s_hdr[f].ok || (dbg & 4)) continue;
-        const uint32_t gf = blockIdx.x * G + f;
-        const clx_frame_desc d = descs[gf];
-        const uint32_t bs = d.block_size, nch = d.n_channels, ca = d.channel_assignment;
-        const int32_t* fbuf = s_buf + (size_t)f * frame_stride;
-        int32_t* o = out + d.out_offset;
-        const SubParams* sp = &s_par[f * CH];
-        const bool vec = ((bs & 3) == 0) && ((d.out_offset & 3) == 0);
-        // Subframes predicted with the i32 accumulator: exact iff sum|coef| * max|sample| < 2^31.
-        for (uint32_t c = 0; c < nch; c++) {
-            const uint32_t absum = sp[c].narrow;
-            if (absum == 0) continue;  // warp-uniform (shared memory broadcast)
-            uint32_t m = 0;
-            const int32_t* cb = fbuf + (size_t)c * bs;
-            for (uint32_t t = threadIdx.x; t < bs; t += blockDim.x) {
-                const int32_t v = cb[t];
-                m = max(m, (uint32_t)(v < 0 ? 0u - (uint32_t)v : (uint32_t)v));
-            }
-            m = __reduce_max_sync(0xffffffffu, m);
-            if ((unsigned long long)absum * m >= (1ull << 31) && lane == 0) {
-                results[gf].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
-                *need_generic = 1;
-            }
-        }
-        if (ca >= 8) {
-            const uint32_t w0 = (uint32_t)sp[0].wasted, w1 = (uint32_t)sp[1].wasted;
-            if (vec) {
-                for (uint32_t t = threadIdx.x * 4; t < bs; t += blockDim.x * 4) {
-                    int4 a = *reinterpret_cast<const int4*>(fbuf + t);
-                    int4 b = *reinterpret_cast<const int4*>(fbuf + bs + t);
-                    int4 x, y;
-                    decor(ca, (int32_t)((uint32_t)a.x << w0), (int32_t)((uint32_t)b.x << w1), x.x, y.x);
-                    decor(ca, (int32_t)((uint32_t)a.y << w0), (int32_t)((uint32_t)b.y << w1), x.y, y.y);
-                    decor(ca, (int32_t)((uint32_t)a.z << w0), (int32_t)((uint32_t)b.z << w1), x.z, y.z);
-                    decor(ca, (int32_t)((uint32_t)a.w << w0), (int32_t)((uint32_t)b.w << w1), x.w, y.w);
-                    *reinterpret_cast<int4*>(o + t) = x;
-                    *reinterpret_cast<int4*>(o + bs + t) = y;
-                }
-            } else {
-                for (uint32_t t = threadIdx.x; t < bs; t += blockDim.x) {
-                    int32_t x, y;
-                    decor(ca, (int32_t)((uint32_t)fbuf[t] << w0), (int32_t)((uint32_t)fbuf[bs + t] << w1), x, y);
-                    o[t] = x;
-                    o[bs + t] = y;
-                }
-            }
-        } else {
-            for (uint32_t c = 0; c < nch; c++) {
-                const uint32_t wst = (uint32_t)sp[c].wasted;
-                const int32_t* cb = fbuf + (size_t)c * bs;
-                int32_t* oc = o + (size_t)c * bs;
-                if (vec) {
-                    for (uint32_t t = threadIdx.x * 4; t < bs; t += blockDim.x * 4) {
-                        int4 a = *reinterpret_cast<const int4*>(cb + t);
-                        a.x = (int32_t)((uint32_t)a.x << wst); a.y = (int32_t)((uint32_t)a.y << wst);
-                        a.z = (int32_t)((uint32_t)a.z << wst); a.w = (int32_t)((uint32_t)a.w << wst);
-                        *reinterpret_cast<int4*>(oc + t) = a;
-                    }
-                } else {
-                    for (uint32_t t = threadIdx.x; t < bs; t += blockDim.x) oc[t] = (int32_t)((uint32_t)cb[t] << wst);
-                }
-            }
-        }
+    } else {
+        if (max_order <= 4) predict_rows<4, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else if (max_order <= 8) predict_rows<8, 8, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else if (max_order <= 12) predict_rows<12, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        else predict_rows<32, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
     }
 }
 
 // ---------------------------------------------------------------------------------
-// launch helper: returns false when the batch cannot use this kernel (G would be 0)
+// launch helpers
 // ---------------------------------------------------------------------------------
 bool coop_plan(uint32_t max_frame_elems, uint32_t max_channels, uint32_t n_frames, int sm_count, size_t smem_budget,
                CoopPlan* plan) {
+    (void)sm_count; (void)smem_budget;
     plan->G = 0;
     if (max_frame_elems == 0 || n_frames == 0 || max_channels == 0 || max_channels > COOP_MAX_CH) return false;
-    const uint32_t stride = ((max_frame_elems + 3) & ~3u) + 4;  // +4 words: frames land on different banks
-    const size_t per_frame = (size_t)stride * 4 + max_channels * sizeof(SubParams) + sizeof(GroupHeader);
-    uint32_t g = (uint32_t)std::min<size_t>(COOP_MAX_G, smem_budget / per_frame);
-    if (g == 0) return false;
-    // fill the machine in as few waves as possible, then prefer small groups (more CTAs in flight)
-    const uint32_t want = (n_frames + (uint32_t)sm_count - 1) / (uint32_t)sm_count;
-    if (want < g) g = std::max<uint32_t>(1, want);
-    plan->G = g;
-    plan->frame_stride = stride;
-    plan->channels = max_channels;
-    plan->smem_bytes = (size_t)g * per_frame;
+    uint32_t ch = 1;
+    while (ch < max_channels) ch <<= 1;  // channel slots per frame: a power of two, so a warp holds whole frames
+    plan->G = 1;
+    plan->channels = ch;
+    plan->frame_stride = 0;
+    plan->smem_bytes = 0;
     return true;
 }
 
+size_t coop_params_bytes(const CoopPlan& plan, uint32_t n_frames) {
+    return plan.G ? (size_t)n_frames * plan.channels * sizeof(SubParams) : 0;
+}
+
 cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
-                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, const CoopPlan& plan,
-                        cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decode_frames_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    static const uint32_t dbg = getenv("CLX_COOP_DEBUG") ? (uint32_t)atoi(getenv("CLX_COOP_DEBUG")) : 0u;
-    dim3 grid((n_frames + plan.G - 1) / plan.G), block(32 * plan.G);
-    decode_frames_coop_kernel<<<grid, block, plan.smem_bytes, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out,
-                                                                        d_results, d_need_generic, plan.G,
-                                                                        plan.frame_stride, plan.channels, dbg);
+                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
+                        const CoopPlan& plan, cudaStream_t stream) {
+    SubParams* params = reinterpret_cast<SubParams*>(d_params);
+    const uint32_t CH = plan.channels;
+    dim3 g1((n_frames + ENT_WARPS - 1) / ENT_WARPS), b1(ENT_WARPS * 32);
+    entropy_frames_kernel<<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH,
+                                                 d_need_generic);
+    const uint64_t slots = (uint64_t)n_frames * CH;
+    dim3 g2((uint32_t)((slots + PRE_WARPS * 32 - 1) / (PRE_WARPS * 32))), b2(PRE_WARPS * 32);
+    predict_frames_kernel<<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, CH, d_need_generic);
     return cudaGetLastError();
 }
 
 }  // namespace clx
 
-extern "C" void clx_debug_coop_stats(unsigned long long* out8, int reset) {
-    cudaMemcpyFromSymbol(out8, clx::g_coop_stats, sizeof(unsigned long long) * 16);
+extern "C" void clx_debug_coop_stats(unsigned long long* out16, int reset) {
+    cudaMemcpyFromSymbol(out16, clx::g_coop_stats, sizeof(unsigned long long) * 16);
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(clx::g_coop_stats, z, sizeof z); }
 }

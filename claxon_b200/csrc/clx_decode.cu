@@ -689,7 +689,7 @@ decode_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes,
 // ---------------------------------------------------------------------------------
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
-                          const CoopPlan& plan, cudaStream_t stream, uint64_t* launches) {
+                          void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches) {
     if (n_frames == 0) return cudaSuccess;
     const uint32_t per_cta = WARPS_PER_CTA * 32;
     dim3 grid((n_frames + per_cta - 1) / per_cta), block(per_cta);
@@ -697,12 +697,12 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
     int* d_need_hi = d_flags + 1;  // set by the 12-tap generic instance: some frames need 32 taps
     cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
-    if (plan.G > 0) {
-        e = launch_coop(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, plan, stream);
+    if (plan.G > 0 && d_params != nullptr) {
+        e = launch_coop(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, d_params, plan, stream);
         if (e != cudaSuccess) return e;
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, d_generic, CLX_INTERNAL_NEED_GENERIC);
-        if (launches) *launches += 1;
+        if (launches) *launches += 2;
     } else {
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, nullptr, 0);

@@ -13,23 +13,25 @@
 #define CLX_INTERNAL_NEED_GENERIC (-2)
 
 namespace clx {
-struct CoopPlan {          // how a batch maps onto the cooperative kernel (G == 0: not at all)
-    uint32_t G = 0;        // frames per CTA (one warp each)
-    uint32_t frame_stride = 0;  // i32 elements of shared memory per frame
-    uint32_t channels = 0;      // channel slots per frame
+struct CoopPlan {          // whether / how a batch uses the fast path (G == 0: generic kernel only)
+    uint32_t G = 0;
+    uint32_t frame_stride = 0;
+    uint32_t channels = 0;      // channel slots per frame (power of two >= max channels in the batch)
     size_t smem_bytes = 0;
 };
 bool coop_plan(uint32_t max_frame_elems, uint32_t max_channels, uint32_t n_frames, int sm_count, size_t smem_budget,
                CoopPlan* plan);
+// Bytes of per-subframe parameter scratch the fast path needs for `n_frames` frames.
+size_t coop_params_bytes(const CoopPlan& plan, uint32_t n_frames);
 cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
-                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, const CoopPlan& plan,
-                        cudaStream_t stream);
+                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
+                        const CoopPlan& plan, cudaStream_t stream);
 // Decodes `n_frames` frames described by d_descs from d_bytes (256-byte aligned; buf_bytes = allocated
 // size, a multiple of 64 with at least 128 bytes of slack after the last frame) into
 // d_out / d_results on `stream`.  d_need_hi is a 4-byte device scratch word.
 // d_flags: two device ints of scratch.  `plan` (may have G == 0) selects the cooperative fast path.
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
-                          const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
+                          void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
 }  // namespace clx
 #endif

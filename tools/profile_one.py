@@ -25,8 +25,8 @@ L = _lib.load()
 st = (ctypes.c_ulonglong * 16)()
 L.clx_debug_coop_stats(st, 1)
 w = max(1, st[0])
-print("coop stats: windows", st[0], "rounds/window", st[1]/w, "spec trips/window", st[2]/w, "merge trips/round", st[3]/max(1,st[1]), "codes/window", st[4]/w)
+if st[0]: print("coop stats: windows", st[0], "rounds/window", st[1]/w, "spec trips/window", st[2]/w, "merge trips/round", st[3]/max(1,st[1]), "codes/window", st[4]/w)
 
-print("cycles/window: spec", st[5]/w, "rounds", st[6]/w, "ranks", st[7]/w, "emit", st[8]/w, "advance", st[9]/w, "| phase1 cycles/warp", st[10]/max(1, 1024*reps), "windows/warp", w/(1024*reps))
+if st[0]: print("cycles/window: spec", st[5]/w, "rounds", st[6]/w, "ranks", st[7]/w, "emit", st[8]/w, "advance", st[9]/w, "| phase1 cycles/warp", st[10]/max(1, 1024*reps), "windows/warp", w/(1024*reps))
 
-print("predict calls", st[13], "narrow", st[12], "cycles/call", st[11]/max(1, st[13]))
+if st[13]: print("predict calls", st[13], "narrow", st[12], "cycles/call", st[11]/max(1, st[13]))
