@@ -213,7 +213,7 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
     // chunk i-1 overlap the kernels of chunk i.  A chunk covers a contiguous byte range and a
     // contiguous output range (descriptors in stream order, as the demuxer emits them).
     const size_t ns = ctx->streams.size();
-    size_t n_chunks = std::min<size_t>(ns, std::max<size_t>(1, n_frames / 256));
+    size_t n_chunks = std::min<size_t>(ns, std::max<size_t>(1, n_frames / 128));
     for (size_t i = 1; i < n_frames && n_chunks > 1; i++)  // chunking needs stream order on both sides
         if (descs[i].byte_offset < descs[i - 1].byte_offset || descs[i].out_offset < descs[i - 1].out_offset)
             n_chunks = 1;

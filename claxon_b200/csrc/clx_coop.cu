@@ -382,8 +382,10 @@ __device__ __forceinline__ int32_t decor_lane(uint32_t own, uint32_t other, uint
 }
 
 constexpr int ENT_WARPS = 4;   // entropy kernel: frames (warps) per CTA
-constexpr int PRE_WARPS = 4;   // predict kernel: warps per CTA
+constexpr int PRE_WARPS = 2;   // predict kernel: warps per CTA
 constexpr int COOP_MAX_CH = 8;
+constexpr int RING_SAMPLES = 64;                 // predict kernel: residual ring per lane
+constexpr int RING_LANE_WORDS = RING_SAMPLES + 4; // +16 bytes of skew: 16-byte accesses of 8 lanes hit 32 banks
 
 // ---------------------------------------------------------------------------------
 // Kernel 1: entropy decode, one warp per frame, output block written in place
@@ -595,7 +597,8 @@ __device__ __forceinline__ void flush_rows(const int32_t* tile, const PredRow* r
 template <int TAPS, int U, typename ACC>
 __device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, uint32_t bs, uint32_t order, uint32_t shift,
                                              uint32_t wasted, uint32_t ca, bool second, const int16_t* coefs, bool active,
-                                             int32_t* tile, const PredRow* rows, uint32_t lane, int32_t& smin, int32_t& smax) {
+                                             int32_t* tile, const PredRow* rows, int32_t* ring, uint32_t lane, int32_t& smin,
+                                             int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
     for (int j = 0; j < TAPS; j++) {
@@ -645,22 +648,32 @@ __device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, ui
         int32_t v[TAPS + U];
 #pragma unroll
         for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
-        // residuals are fetched as 16-byte vectors two trips ahead (idle lanes read lane-0-ish data:
-        // `src` of an idle lane aliases an active one)
-        constexpr int Q = U / 4;
-        int4 r1[Q], r2[Q];
+        // Residuals stream HBM/L2 -> shared memory through a per-lane ring filled by cp.async
+        // (LDGSTS, 16 bytes per copy) DEPTH trips ahead of their use, so neither DRAM nor L2 latency
+        // is ever waited for; idle lanes copy some active lane's data and ignore it.
+        constexpr int Q = U / 4;                 // 16-byte copies per trip
+        constexpr int SLOTS = RING_SAMPLES / U;  // trips the ring holds
+        constexpr int DEPTH = SLOTS - 2;         // trips in flight
+        const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+        auto request = [&](uint32_t trip) {      // trip index relative to head_end
+            const uint32_t t = min(head_end + trip * U, bulk_end - U);
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            r1[q] = *reinterpret_cast<const int4*>(src + head_end + 4 * q);
-            r2[q] = *reinterpret_cast<const int4*>(src + min(head_end + U + 4 * q, bulk_end - 4));
-        }
-        for (uint32_t t = head_end; t < bulk_end; t += U) {
+            for (int q = 0; q < Q; q++)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring_s + ((trip % SLOTS) * U + 4 * q) * 4),
+                             "l"(src + t + 4 * q));
+            asm volatile("cp.async.commit_group;");
+        };
+#pragma unroll
+        for (int p = 0; p < DEPTH; p++) request(p);
+        uint32_t trip = 0;
+        for (uint32_t t = head_end; t < bulk_end; t += U, trip++) {
+            request(trip + DEPTH);
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH));
             int32_t r[U];
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                r[4 * q] = r1[q].x; r[4 * q + 1] = r1[q].y; r[4 * q + 2] = r1[q].z; r[4 * q + 3] = r1[q].w;
-                r1[q] = r2[q];
-                r2[q] = *reinterpret_cast<const int4*>(src + min(t + 2 * U + 4 * q, bulk_end - 4));
+                const int4 x = *reinterpret_cast<const int4*>(ring + (trip % SLOTS) * U + 4 * q);
+                r[4 * q] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
             }
             predict_trip<TAPS, U, ACC>(v, c, r, shift);
 #pragma unroll
@@ -687,6 +700,7 @@ __device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, ui
         }
 #pragma unroll
         for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
+        asm volatile("cp.async.wait_group 0;");  // the look-ahead copies past the bulk are never used
     }
     guarded(bulk_end, max_bs);
     if (max_bs & 31) flush_rows(tile, rows, max_bs & ~31u, lane);
@@ -698,6 +712,7 @@ predict_frames_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frame
                       int* __restrict__ need_generic) {
     __shared__ __align__(16) int32_t s_tile[PRE_WARPS][32 * 32];
     __shared__ __align__(16) PredRow s_rows[PRE_WARPS][32];
+    __shared__ __align__(16) int32_t s_ring[PRE_WARPS][32 * RING_LANE_WORDS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = (blockIdx.x * PRE_WARPS + warp) * 32 + lane;  // CH is a power of two: frames never split
     const uint32_t f = slot / CH, c = slot % CH;
@@ -745,10 +760,10 @@ predict_frames_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frame
     const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
     int32_t smin = 0, smax = 0;
     if (all_narrow) {
-        if (max_order <= 4) predict_rows<4, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else if (max_order <= 8) predict_rows<8, 8, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else if (max_order <= 12) predict_rows<12, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else predict_rows<32, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        if (max_order <= 4) predict_rows<4, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else if (max_order <= 8) predict_rows<8, 8, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else if (max_order <= 12) predict_rows<12, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else predict_rows<32, 4, int>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
         // exactness of the i32 accumulator: sum|coef| * max|sample| < 2^31 over the samples produced
         const uint32_t m = max((uint32_t)smax, 0u - (uint32_t)smin);
         if (active && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) {
@@ -756,10 +771,10 @@ predict_frames_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frame
             *need_generic = 1;
         }
     } else {
-        if (max_order <= 4) predict_rows<4, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else if (max_order <= 8) predict_rows<8, 8, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else if (max_order <= 12) predict_rows<12, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
-        else predict_rows<32, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, lane, smin, smax);
+        if (max_order <= 4) predict_rows<4, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else if (max_order <= 8) predict_rows<8, 8, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else if (max_order <= 12) predict_rows<12, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
+        else predict_rows<32, 4, long long>(src, bs, order, shift, wasted, ca, second, coefs, active, tile, rows, s_ring[warp] + lane * RING_LANE_WORDS, lane, smin, smax);
     }
 }
 
