@@ -144,78 +144,50 @@ __device__ __forceinline__ int32_t sext(uint32_t v, uint32_t bits) {
 // ---------------------------------------------------------------------------------
 // Rice decode of one window.  Vocabulary: a *search* looks for the next unary terminator (a 1 bit)
 // from some bit offset; after a terminator at t the next search starts at t+1+k.  The *phase* of a
-// 32-bit word is the offset at which the first search inside it starts.  A word walked from phase e
-// yields its terminator mask and its exit phase (the next word's entry phase).
+// lane is the offset (into its first word) at which the first search inside its 128-bit span
+// starts; walking the span from a phase yields the terminator masks of its words and the exit phase
+// (the next lane's entry phase).
 //
-// Every lane owns WPL consecutive words and walks them simultaneously (independent dependency
-// chains, interleaved by the unrolled loop).  Phases are first speculated — every word assumes its
-// left neighbour exits as it would from phase 0 — and then corrected by a fix-point: a word whose
-// entry phase changed is re-walked, but only until it meets a terminator of its own phase-0 chain,
-// from where both chains coincide.
+// Every lane first walks its span for the *speculated* phase 0.  A shuffle fix-point then makes the
+// phases exact: a lane whose entry phase turns out different re-walks, but only until it meets a
+// terminator of its own speculated chain — from there on both chains coincide — so a correction
+// costs a couple of codes, and since 128 bits hold many codes almost every re-walk does merge and
+// the fix-point settles in one or two rounds.
 // ---------------------------------------------------------------------------------
-#ifdef CLX_COOP_STATS
-#define COOP_STAT(i, v) do { const unsigned long long sv_ = (unsigned long long)(v); if (lane == 0) atomicAdd(&g_coop_stats[i], sv_); } while (0)
-#define COOP_CLOCK() clock64()
-#else
-#define COOP_STAT(i, v) do { (void)(v); } while (0)
-#define COOP_CLOCK() 0ll
-#endif
-
-struct Walk {
+struct LaneWalk {
     uint32_t tm[WPL];  // terminator masks (bit 31 = first bit of the word)
-    uint32_t x[WPL];   // exit phases
+    uint32_t x;        // exit phase
 };
 
-// select without control flow: the optimiser otherwise turns chains of ?: back into branches, which
-// serialises the WPL interleaved walks of a lane.
-__device__ __forceinline__ uint32_t sel32(bool c, uint32_t a, uint32_t b) {
-    uint32_t r;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
-    return r;
-}
-
-// One code of one word, branch-free (everything is a select, so the WPL words of a lane interleave
-// in the instruction stream and their dependency chains overlap).  `o` = current search offset,
-// 64 once the word is finished.  `stm` = speculated terminator mask to merge with (0: never merge).
-__device__ __forceinline__ void walk_step(uint32_t W, uint32_t k, uint32_t stm, uint32_t sx, uint32_t& o, uint32_t& tm,
-                                          uint32_t& x) {
-    const bool active = o < 32;
-    const uint32_t m = W & __funnelshift_rc(0xffffffffu, 0u, o);  // o >= 32 -> 0
-    const uint32_t t = __clz(m);                                   // 32 when nothing is left
-    const uint32_t bit = __funnelshift_rc(0x80000000u, 0u, t);     // 0 when nothing is left
-    const bool hit = bit != 0;
-    const bool mrg = (stm & bit) != 0;
-    const uint32_t no = t + 1 + k;
-    const bool spill = no >= 32;
-    tm |= sel32(mrg, stm & (bit | (bit - 1)), bit);
-    x = sel32(mrg, sx, sel32(hit, sel32(spill, no - 32, x), sel32(active, 0u, x)));
-    o = sel32(active && hit && !mrg && !spill, no, 64u);
-}
-
-// Walks the words flagged in `todo` from phases e[]; when `merge`, a walk stops at the first
-// terminator shared with the speculated chain.  Results for unflagged words are left untouched.
-__device__ __forceinline__ uint32_t walk_words(const uint32_t (&W)[WPL], const uint32_t (&e)[WPL], uint32_t k, uint32_t todo,
-                                           bool merge, const Walk& spec, Walk& out) {
-    uint32_t trips = 0;
-    uint32_t o[WPL];
+// Walks the lane's words from word `j0`, phase `e`.  When `merge`, stops at the first terminator
+// shared with the speculated walk and adopts its remainder.
+__device__ __forceinline__ void walk_lane(const uint32_t (&W)[WPL], uint32_t j0, uint32_t e, uint32_t k, bool merge,
+                                          const LaneWalk& spec, LaneWalk& out) {
+    uint32_t o = e;
+    bool merged = false;
 #pragma unroll
     for (uint32_t j = 0; j < WPL; j++) {
-        const bool go = (todo >> j) & 1u;
-        o[j] = sel32(go, e[j], 64u);
-        out.tm[j] = sel32(go, 0u, out.tm[j]);
-        out.x[j] = sel32(go, 0u, out.x[j]);
+        uint32_t tm = 0;
+        if (merged) tm = spec.tm[j];
+        else if (j >= j0) {
+            while (o < 32) {
+                const uint32_t m = W[j] & (0xffffffffu >> o);
+                if (m == 0) { o = 32; break; }  // the search carries on in the next word, phase 0
+                const uint32_t t = __clz(m);
+                const uint32_t bit = 0x80000000u >> t;
+                if (merge && (spec.tm[j] & bit)) {
+                    tm |= spec.tm[j] & (bit | (bit - 1));
+                    merged = true;
+                    break;
+                }
+                tm |= bit;
+                o = t + 1 + k;
+            }
+            if (!merged) o -= 32;
+        }
+        out.tm[j] = tm;
     }
-    for (;;) {
-#pragma unroll
-        for (uint32_t j = 0; j < WPL; j++)
-            walk_step(W[j], k, merge ? spec.tm[j] : 0u, spec.x[j], o[j], out.tm[j], out.x[j]);
-        bool more = false;
-#pragma unroll
-        for (uint32_t j = 0; j < WPL; j++) more |= o[j] < 32;
-        trips++;
-        if (!__any_sync(0xffffffffu, more)) break;
-    }
-    return trips;
+    out.x = merged ? spec.x : o;
 }
 
 // Decodes up to `n_rem` Rice codes with parameter k starting at bit `P` from the current window
@@ -225,50 +197,31 @@ __device__ __forceinline__ uint32_t walk_words(const uint32_t (&W)[WPL], const u
 __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint32_t k, uint32_t n_rem, int32_t* out,
                                                 uint32_t lane) {
     const uint32_t s = P - (w.b0 << 5);      // < 128: where the first search starts
-    const uint32_t first = s >> 5;           // virtual word that contains it (lane 0)
+    const uint32_t first = s >> 5;           // lane 0's word that contains it
     uint32_t W[WPL], WN[WPL];
 #pragma unroll
     for (uint32_t j = 0; j < WPL; j++) W[j] = w.X[j];
     const uint32_t right = __shfl_down_sync(0xffffffffu, w.X[0], 1);
 #pragma unroll
     for (uint32_t j = 0; j < WPL; j++) WN[j] = j + 1 < WPL ? w.X[j + 1] : right;
-    // words that take part: from `first` up to the last-but-one word of the window
-    uint32_t live = (1u << WPL) - 1u;
-    if (lane == 0) live &= ~((1u << first) - 1u);
-    if (lane == 31) live &= ~(1u << (WPL - 1));
-#pragma unroll
-    for (uint32_t j = 0; j < WPL; j++)
-        if (!(live & (1u << j))) W[j] = 0;  // a dead word has no terminators and exits with phase 0
+    if (lane == 31) W[WPL - 1] = 0;  // lent only: no terminators of its own
 
-    long long tc0 = COOP_CLOCK();
-    // 1. speculated chains: phase 0 everywhere
-    Walk spec, cur;
-    const uint32_t zero[WPL] = {0, 0, 0, 0};
-    COOP_STAT(0, 1);
-    COOP_STAT(2, walk_words(W, zero, k, live, false, spec, spec));
-#pragma unroll
-    for (uint32_t j = 0; j < WPL; j++)
-        if (!(live & (1u << j))) { spec.tm[j] = 0; spec.x[j] = 0; }
+    // 1. speculated walk: phase 0 (lane 0 knows its true start)
+    LaneWalk spec, cur;
+    const uint32_t j0 = lane == 0 ? first : 0u;
+    uint32_t e = lane == 0 ? (s & 31u) : 0u;
+    walk_lane(W, j0, e, k, false, spec, spec);
     cur = spec;
-    long long tc1 = COOP_CLOCK(); COOP_STAT(5, tc1 - tc0);
     // 2. fix-point on the entry phases
-    uint32_t e[WPL] = {0, 0, 0, 0};
     for (;;) {
-        const uint32_t left = __shfl_up_sync(0xffffffffu, cur.x[WPL - 1], 1);
-        uint32_t todo = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < WPL; j++) {
-            uint32_t want = j == 0 ? left : cur.x[j - 1];
-            if (lane == 0 && j <= first) want = j == first ? (s & 31) : 0;
-            if (!(live & (1u << j))) want = 0;
-            if (want != e[j]) { e[j] = want; todo |= 1u << j; }
+        const uint32_t left = __shfl_up_sync(0xffffffffu, cur.x, 1);
+        const bool redo = lane > 0 && left != e;
+        if (!__any_sync(0xffffffffu, redo)) break;
+        if (redo) {
+            e = left;
+            walk_lane(W, 0, e, k, true, spec, cur);
         }
-        todo &= live;
-        if (!__any_sync(0xffffffffu, todo != 0)) break;
-        COOP_STAT(1, 1);
-        COOP_STAT(3, walk_words(W, e, k, todo, true, spec, cur));
     }
-    long long tc2 = COOP_CLOCK(); COOP_STAT(6, tc2 - tc1);
     // 3. ranks
     uint32_t cnt[WPL], lane_cnt = 0;
 #pragma unroll
@@ -301,55 +254,38 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
         total = n_rem;
     }
     if (total == 0) return 0;
-    // 4. end of the last code at or before each word (window-relative bit offsets)
-    uint32_t wend[WPL], lane_end = 0;
+    // 4. end of the last code at or before each lane (window-relative bit offsets)
+    uint32_t lane_end = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < WPL; j++) {
-        wend[j] = cur.tm[j] ? ((lane * WPL + j) << 5) + (32 - __ffs(cur.tm[j])) + 1 + k : 0;
-        lane_end = max(lane_end, wend[j]);
-    }
+    for (uint32_t j = 0; j < WPL; j++)
+        if (cur.tm[j]) lane_end = ((lane * WPL + j) << 5) + (32 - __ffs(cur.tm[j])) + 1 + k;
     uint32_t endi = lane_end;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, endi, d);
         if (lane >= (uint32_t)d) endi = max(endi, v);
     }
-    uint32_t before = __shfl_up_sync(0xffffffffu, endi, 1);
-    if (lane == 0) before = 0;
+    uint32_t start = __shfl_up_sync(0xffffffffu, endi, 1);
+    if (lane == 0) start = 0;
+    start = max(start, s);
     const uint32_t new_end = __shfl_sync(0xffffffffu, endi, 31);
-    uint32_t start[WPL];
-    start[0] = max(before, s);
+    // 5. emit, word after word
+    uint32_t idx = rank[0];
 #pragma unroll
-    for (uint32_t j = 1; j < WPL; j++) start[j] = max(start[j - 1], wend[j - 1]);
-    long long tc3 = COOP_CLOCK(); COOP_STAT(7, tc3 - tc2);
-    // 5. emit: the WPL words of a lane advance together, one code each per trip (predicated)
-    uint32_t rest[WPL];
-#pragma unroll
-    for (uint32_t j = 0; j < WPL; j++) rest[j] = cur.tm[j];
-    for (;;) {
-        bool more = false;
-#pragma unroll
-        for (uint32_t j = 0; j < WPL; j++) {
-            const bool have = rest[j] != 0;
-            const uint32_t t = __clz(rest[j]) & 31;
-            rest[j] &= ~__funnelshift_rc(0x80000000u, 0u, sel32(have, t, 32u));
+    for (uint32_t j = 0; j < WPL; j++) {
+        uint32_t rest = cur.tm[j];
+        while (rest) {
+            const uint32_t t = __clz(rest);
+            rest &= ~(0x80000000u >> t);
             const uint32_t pos = ((lane * WPL + j) << 5) + t;
-            const uint32_t q = pos - start[j];
+            const uint32_t q = pos - start;
             const uint32_t hi = __funnelshift_lc(WN[j], W[j], t + 1);
             const uint32_t r = __funnelshift_l(hi, 0, k);
             const uint32_t u = (q << k) | r;
-            const uint32_t val = (u >> 1) ^ (0u - (u & 1u));
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.u32 [%0], %1;\n\t}" ::"l"(out + rank[j]), "r"(val),
-                         "r"((uint32_t)have)
-                         : "memory");
-            rank[j] += (uint32_t)have;
-            start[j] = sel32(have, pos + 1 + k, start[j]);
-            more |= rest[j] != 0;
+            out[idx++] = (int32_t)((u >> 1) ^ (0u - (u & 1u)));
+            start = pos + 1 + k;
         }
-        if (!__any_sync(0xffffffffu, more)) break;
     }
-    COOP_STAT(4, total);
-    COOP_STAT(8, COOP_CLOCK() - tc3);
     P = (w.b0 << 5) + new_end;
     return total;
 }
