@@ -58,6 +58,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             return LIB  # GPU box without a toolchain: use the prebuilt library that travelled
         raise RuntimeError("nvcc not found and no prebuilt libclaxon_b200.so")
     extra = ["-DCLX_COOP_STATS"] if os.environ.get("CLX_COOP_STATS") else []
+    if os.environ.get("CLX_EXPERIMENT"):
+        extra.append("-DCLX_EXPERIMENT")
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB, *lib_sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

@@ -58,6 +58,7 @@ struct SubParams {   // one per subframe (global memory, written by the entropy 
 // ---------------------------------------------------------------------------------
 __device__ unsigned long long g_coop_stats[16];  // debug counters
 constexpr uint32_t WPL = 4;            // words per lane
+constexpr uint32_t STAGE_CODES = 1024;  // codes one window may emit (a window with more is cut short)
 constexpr uint32_t WIN_WORDS = 32 * WPL;
 
 struct Win {
@@ -195,7 +196,8 @@ __device__ __forceinline__ void walk_lane(const uint32_t (&W)[WPL], uint32_t j0,
 // the end of the last decoded code.  The very last word of the window is never owned (it only
 // lends its bits as the right-hand neighbour), so Y is not read here.
 __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint32_t k, uint32_t n_rem, int32_t* out,
-                                                uint32_t lane) {
+                                                int32_t* stage, uint32_t lane) {
+    n_rem = min(n_rem, STAGE_CODES);
     const uint32_t s = P - (w.b0 << 5);      // < 128: where the first search starts
     const uint32_t first = s >> 5;           // lane 0's word that contains it
     uint32_t W[WPL], WN[WPL];
@@ -269,8 +271,11 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
     if (lane == 0) start = 0;
     start = max(start, s);
     const uint32_t new_end = __shfl_sync(0xffffffffu, endi, 31);
-    // 5. emit, word after word
-    uint32_t idx = rank[0];
+    // 5. emit, word after word, into the warp's staging buffer.  A lane's codes are consecutive in
+    // the output but 32 lanes' stores would touch 32 different sectors; staged, the window leaves
+    // as full 16-byte vectors.  Staging index and global element index agree modulo 4.
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) >> 2) & 3u;
+    uint32_t idx = mis + rank[0];
 #pragma unroll
     for (uint32_t j = 0; j < WPL; j++) {
         uint32_t rest = cur.tm[j];
@@ -282,10 +287,25 @@ __device__ __forceinline__ uint32_t rice_window(const Win& w, uint32_t& P, uint3
             const uint32_t hi = __funnelshift_lc(WN[j], W[j], t + 1);
             const uint32_t r = __funnelshift_l(hi, 0, k);
             const uint32_t u = (q << k) | r;
-            out[idx++] = (int32_t)((u >> 1) ^ (0u - (u & 1u)));
+            stage[idx++] = (int32_t)((u >> 1) ^ (0u - (u & 1u)));
             start = pos + 1 + k;
         }
     }
+    __syncwarp();
+    // 6. flush: group g holds staging words [4g, 4g+4) = output elements [4g - mis, 4g - mis + 4)
+    const uint32_t hi_idx = mis + total;
+    for (uint32_t g4 = lane * 4; g4 < hi_idx; g4 += 128) {
+        const int4 v = *reinterpret_cast<const int4*>(stage + g4);
+        int32_t* dst = out + g4 - mis;   // 16-byte aligned by construction
+        if (g4 >= mis && g4 + 4 <= hi_idx) *reinterpret_cast<int4*>(dst) = v;
+        else {
+            if (g4 >= mis && g4 < hi_idx) dst[0] = v.x;
+            if (g4 + 1 >= mis && g4 + 1 < hi_idx) dst[1] = v.y;
+            if (g4 + 2 >= mis && g4 + 2 < hi_idx) dst[2] = v.z;
+            if (g4 + 3 < hi_idx) dst[3] = v.w;
+        }
+    }
+    __syncwarp();
     P = (w.b0 << 5) + new_end;
     return total;
 }
@@ -302,19 +322,27 @@ __device__ __forceinline__ void decor(uint32_t ca, int32_t a, int32_t b, int32_t
 }
 
 // Per-lane, branch-free form for the predict kernel: the lane holds one channel's sample `own`, its
-// neighbour's is `other`; masks are all-ones / zero and loop invariant (m_sec: this lane is channel 1;
-// m_ls / m_rs / m_ms: the frame's channel assignment).  Returns this lane's decorrelated sample.
-__device__ __forceinline__ int32_t decor_lane(uint32_t own, uint32_t other, uint32_t m_sec, uint32_t m_ls, uint32_t m_rs,
-                                              uint32_t m_ms) {
-    const uint32_t a = (m_sec & other) | (~m_sec & own);   // channel 0 value
-    const uint32_t b = (m_sec & own) | (~m_sec & other);   // channel 1 value
-    const uint32_t bs = (b ^ m_sec) - m_sec;               // +b for channel 0's result, -b for channel 1's
-    const uint32_t mid = (a << 1) | (b & 1u);
-    const uint32_t ms = (uint32_t)(((int32_t)(mid + bs)) >> 1);   // (m + s) / 2 or (m - s) / 2
-    const uint32_t ls = (m_sec & (a - b)) | (~m_sec & a);          // left stays, right = left - side
-    const uint32_t rs = (m_sec & b) | (~m_sec & (a + b));          // left = side + right, right stays
-    const uint32_t any = m_ls | m_rs | m_ms;
-    return (int32_t)((m_ls & ls) | (m_rs & rs) | (m_ms & ms) | (~any & own));
+// neighbour's is `other`.  Every case of src/frame.rs:319-389 is (own*p + other*q + side&1) >> s in
+// wrapping i32 with per-lane constants (side = channel 1's sample):
+//   independent      p= 1 q=0            left/side  ch0: p=1 q=0    ch1 (left - side): p=-1 q=1
+//   side/right ch0 (side + right): p=1 q=1   ch1: p=1 q=0
+//   mid/side   ch0: (2*mid + (side&1) + side) >> 1 : p=2 q=1, bit from other
+//              ch1: (2*mid + (side&1) - side) >> 1 : p=-1 q=2, bit from own
+struct DecorLane { uint32_t p, q, own_bit, other_bit, s; };
+__device__ __forceinline__ DecorLane decor_consts(uint32_t ca, bool second) {
+    DecorLane d = {1u, 0u, 0u, 0u, 0u};
+    if (ca == 8 && second) { d.p = 0xffffffffu; d.q = 1u; }
+    else if (ca == 9 && !second) { d.q = 1u; }
+    else if (ca == 10) {
+        d.s = 1u;
+        if (second) { d.p = 0xffffffffu; d.q = 2u; d.own_bit = 1u; }
+        else { d.p = 2u; d.q = 1u; d.other_bit = 1u; }
+    }
+    return d;
+}
+__device__ __forceinline__ int32_t decor_lane(uint32_t own, uint32_t other, const DecorLane& d) {
+    const uint32_t t = own * d.p + other * d.q + (own & d.own_bit) + (other & d.other_bit);
+    return ((int32_t)t) >> d.s;
 }
 
 constexpr int ENT_WARPS = 4;   // entropy kernel: frames (warps) per CTA
@@ -330,9 +358,11 @@ __global__ void __launch_bounds__(ENT_WARPS * 32)
 entropy_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
                       uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
                       SubParams* __restrict__ params, uint32_t CH, int* __restrict__ need_generic) {
+    __shared__ __align__(16) int32_t s_stage[ENT_WARPS][STAGE_CODES + 4];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t fidx = blockIdx.x * ENT_WARPS + warp;
     if (fidx >= n_frames) return;
+    int32_t* stage = s_stage[warp];
     const clx_frame_desc d = descs[fidx];
     const uint32_t bs = d.block_size, nch = d.n_channels, ca = d.channel_assignment;
     bool ok = nch <= CH && d.bits_per_sample != 0;
@@ -438,7 +468,7 @@ entropy_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, con
             uint32_t n_rem = part == 0 ? per - order : per;
             while (n_rem > 0) {
                 win_advance(w, P, lane);
-                const uint32_t got = rice_window(w, P, k, n_rem, sbuf + at, lane);
+                const uint32_t got = rice_window(w, P, k, n_rem, sbuf + at, stage, lane);
                 if (got == 0 || P > limit) { ok = false; break; }
                 at += got;
                 n_rem -= got;
@@ -553,12 +583,11 @@ __device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, ui
 
     // emits one finished sample of every lane: wasted shift, decorrelation with the neighbouring lane,
     // staging into the transpose tile, flush every 32 steps
-    const uint32_t m_sec = second ? 0xffffffffu : 0u, m_ls = ca == 8 ? 0xffffffffu : 0u,
-                   m_rs = ca == 9 ? 0xffffffffu : 0u, m_ms = ca == 10 ? 0xffffffffu : 0u;
+    const DecorLane dl = decor_consts(ca, second);
     auto emit = [&](uint32_t t, int32_t s) {
         int32_t o = (int32_t)((uint32_t)s << wasted);
         const int32_t partner = __shfl_xor_sync(0xffffffffu, o, 1);
-        o = decor_lane((uint32_t)o, (uint32_t)partner, m_sec, m_ls, m_rs, m_ms);
+        o = decor_lane((uint32_t)o, (uint32_t)partner, dl);
         tile[tile_word(lane, t & 31)] = o;
         if ((t & 31) == 31) flush_rows(tile, rows, t - 31, lane);
     };
@@ -625,7 +654,7 @@ __device__ __forceinline__ void predict_rows(const int32_t* __restrict__ src, ui
                 for (int i = 0; i < 4; i++) {
                     o[i] = (int32_t)((uint32_t)v[TAPS + 4 * q + i] << wasted);
                     const int32_t partner = __shfl_xor_sync(0xffffffffu, o[i], 1);
-                    o[i] = decor_lane((uint32_t)o[i], (uint32_t)partner, m_sec, m_ls, m_rs, m_ms);
+                    o[i] = decor_lane((uint32_t)o[i], (uint32_t)partner, dl);
                 }
                 const uint32_t col = (t + 4 * q) & 31;
                 *reinterpret_cast<int4*>(tile + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) = make_int4(o[0], o[1], o[2], o[3]);
@@ -748,6 +777,25 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
     predict_frames_kernel<<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, CH, d_need_generic);
     return cudaGetLastError();
 }
+
+#ifdef CLX_EXPERIMENT
+cudaError_t launch_entropy_only(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
+                                int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
+                                const CoopPlan& plan, cudaStream_t stream) {
+    dim3 g1((n_frames + ENT_WARPS - 1) / ENT_WARPS), b1(ENT_WARPS * 32);
+    entropy_frames_kernel<<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
+                                                 reinterpret_cast<SubParams*>(d_params), plan.channels, d_need_generic);
+    return cudaGetLastError();
+}
+cudaError_t launch_predict_only(const clx_frame_desc* d_descs, uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results,
+                                int* d_need_generic, void* d_params, const CoopPlan& plan, cudaStream_t stream) {
+    const uint64_t slots = (uint64_t)n_frames * plan.channels;
+    dim3 g2((uint32_t)((slots + PRE_WARPS * 32 - 1) / (PRE_WARPS * 32))), b2(PRE_WARPS * 32);
+    predict_frames_kernel<<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, reinterpret_cast<SubParams*>(d_params),
+                                                 plan.channels, d_need_generic);
+    return cudaGetLastError();
+}
+#endif
 
 }  // namespace clx
 
