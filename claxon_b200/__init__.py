@@ -19,7 +19,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, FRAME_VARIABLE_BLOCKING,
+from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, OPT_WARP_PER_FRAME,
+                   FRAME_VARIABLE_BLOCKING,
                    FRAME_CRC16_VERIFIED)
 
 __all__ = ["Error", "Block", "FrameReader", "FlacReader", "StreamInfo", "Context", "DeviceBatch",
@@ -164,9 +165,13 @@ def descs_from_offsets(data, offsets, lengths=None, flags: int = 0) -> tuple[np.
 class Context:
     """clx_ctx: one per host thread / GPU. Raises Error(NO_DEVICE) without a usable GPU."""
 
-    def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False):
+    def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False,
+                 warp_per_frame: bool = False):
+        """`generic_only` / `warp_per_frame` select the other device paths (testing, A/B measurements); the
+        default is the lane-per-frame entropy kernel + lane-per-subframe prediction kernel (csrc/clx_seq.cu)."""
         self._L = _lib.load()
-        flags = (0 if verify_crc else OPT_NO_VERIFY_CRC) | (OPT_GENERIC_KERNEL_ONLY if generic_only else 0)
+        flags = ((0 if verify_crc else OPT_NO_VERIFY_CRC) | (OPT_GENERIC_KERNEL_ONLY if generic_only else 0)
+                 | (OPT_WARP_PER_FRAME if warp_per_frame else 0))
         opts = _lib.Options(device, flags, n_streams, 0)
         h = C.c_void_p()
         _check(self._L.clx_ctx_create(C.byref(opts), C.byref(h)))

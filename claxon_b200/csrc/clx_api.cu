@@ -28,6 +28,7 @@ struct clx_ctx {
     int sm_count = 148;
     size_t smem_budget = 227 * 1024;
     bool use_coop = true;
+    bool warp_per_frame = false;  // CLX_OPT_WARP_PER_FRAME: the earlier fast path (clx_coop.cu) instead of clx_seq.cu
     // grow-only device scratch for clx_decode_frames, one set per stream (chunk pipelining)
     struct Scratch {
         uint8_t* d_bytes = nullptr; size_t bytes_cap = 0;
@@ -132,12 +133,18 @@ void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, 
 clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t n) {
     clx::CoopPlan plan;
     if (!ctx->use_coop) return plan;
-    uint32_t max_elems = 0, max_ch = 0;
+    uint32_t max_elems = 0, max_ch = 0, max_bs = 0, max_bps = 0;
     for (size_t i = 0; i < n; i++) {
         max_elems = std::max<uint32_t>(max_elems, (uint32_t)descs[i].n_channels * descs[i].block_size);
         max_ch = std::max<uint32_t>(max_ch, descs[i].n_channels);
+        max_bs = std::max<uint32_t>(max_bs, descs[i].block_size);
+        max_bps = std::max<uint32_t>(max_bps, descs[i].bits_per_sample);
     }
-    clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan);
+    if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame) {
+        plan.G = 2;
+        plan.narrow = max_bps <= 16 ? 1u : 0u;
+        plan.max_bs = max_bs;
+    }
     return plan;
 }
 
@@ -170,6 +177,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
         ctx->smem_budget = prop.sharedMemPerBlockOptin;
     }
     if (opts && (opts->flags & CLX_OPT_GENERIC_KERNEL_ONLY)) ctx->use_coop = false;
+    if (opts && (opts->flags & CLX_OPT_WARP_PER_FRAME)) ctx->warp_per_frame = true;
     ctx->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     *out = ctx;
     return CLX_OK;

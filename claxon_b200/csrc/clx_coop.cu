@@ -761,12 +761,15 @@ bool coop_plan(uint32_t max_frame_elems, uint32_t max_channels, uint32_t n_frame
 }
 
 size_t coop_params_bytes(const CoopPlan& plan, uint32_t n_frames) {
+    if (plan.G == 2) return seq_scratch_bytes(plan, n_frames);
     return plan.G ? (size_t)n_frames * plan.channels * sizeof(SubParams) : 0;
 }
 
 cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
                         int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
                         const CoopPlan& plan, cudaStream_t stream) {
+    if (plan.G == 2)
+        return launch_seq(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_need_generic, d_params, plan, stream, 3);
     SubParams* params = reinterpret_cast<SubParams*>(d_params);
     const uint32_t CH = plan.channels;
     dim3 g1((n_frames + ENT_WARPS - 1) / ENT_WARPS), b1(ENT_WARPS * 32);

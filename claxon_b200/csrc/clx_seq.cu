@@ -1,0 +1,520 @@
+// clx_seq.cu — the fast path of claxon_b200: sequential entropy decode (one lane per frame) +
+// prediction (one lane per subframe), two kernels joined by a warp-interleaved residual scratch.
+//
+//   1. `entropy_seq_kernel` — ONE LANE PER FRAME, 32 frames per warp.  The lane walks its frame's
+//      bitstream in claxon's own order (clx_seq_lane.h: subframe header, warm-up, LPC parameters,
+//      residual header, Rice partitions; reference src/subframe.rs:29-91, :236-380, :382-415,
+//      :651-701) with a three-word register window over a per-lane shared-memory ring that cp.async
+//      keeps 16 quads ahead.  Eight Rice codes per trip: funnel shift, clz, two shifts, one
+//      multiply-add, rice_to_signed — about 12 instructions per code, every lane busy.  Residuals go
+//      to the scratch as one 16-byte store per eight codes (i16 for streams of <= 16 bits, else
+//      two stores of i32), laid out so that a warp's stores form whole 512-byte rows.
+//   2. `predict_seq_kernel` — ONE LANE PER SUBFRAME.  predict_fixed / predict_lpc_* (src/subframe.rs:
+//      417-474, :524-614) are strictly serial recurrences (the floor in `>> qlp_shift` makes them
+//      non-associative), so the parallel axis is the set of subframes: coefficients and history
+//      register-resident, residual rows prefetched by cp.async six trips ahead (coalesced), eight
+//      samples per trip.  Samples leave through a swizzled 32x32 shared-memory transpose; the flush
+//      handles the two channels of a frame together, which turns the wasted-bits shift
+//      (src/subframe.rs:216-225) and the inter-channel decorrelation (src/frame.rs:319-389) into a
+//      few operations per PAIR of 16-byte vectors, and writes planar i32 as coalesced 16-byte stores.
+//
+// Anything irregular is flagged (CLX_INTERNAL_NEED_GENERIC) and decoded by the generic kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "claxon_b200.h"
+#include "clx_internal.h"
+#include "clx_seq_lane.h"
+
+namespace clx {
+
+// ---------------------------------------------------------------------------------
+// Device IO policy of the entropy lane
+// ---------------------------------------------------------------------------------
+constexpr uint32_t RQ = 16;           // ring: quads (16 bytes) per lane
+constexpr int ENT_SEQ_WARPS = 1;      // warps (of 32 frames) per CTA
+
+struct DeviceIO {
+    uint32_t ring;        // shared-space byte address of the lane's ring (256 bytes, 256-byte aligned)
+    uint32_t rot;         // 16 * (lane & 7): rotates the ring index so that lanes in step hit different banks
+    const uint4* gbase;   // the frame's 16-byte aligned base
+    uint32_t qlim;        // quads readable from gbase (beyond: zeros)
+    uint32_t fq;          // next quad to request
+    uint32_t wp;          // ring byte offset (unmasked) of the next word of the register window
+    char* rows0;          // channel 0's rows + lane * 16
+    char* column;         // current channel's column
+    uint64_t channel_stride;
+
+    __device__ __forceinline__ void issue(uint32_t q) {
+        const uint32_t dst = ring | (((q << 4) + rot) & 0xF0u);
+        const bool in = q < qlim;
+        const uint4* src = gbase + (in ? q : 0u);
+        const uint32_t sz = in ? 16u : 0u;  // src-size 0: the destination is zero-filled
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t wi) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (((wi << 2) + rot) & 0xFCu)) : "memory");
+        return __byte_perm(v, 0, 0x0123);
+    }
+    __device__ __forceinline__ void seek_next(uint32_t wi) { wp = (wi << 2) + rot; }
+    __device__ __forceinline__ uint32_t next_word() {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (wp & 0xFCu)) : "memory");
+        wp += 4;
+        return __byte_perm(v, 0, 0x0123);
+    }
+    // Random access (headers, slow codes): the ring covers quads [bitpos >> 7, (bitpos >> 7) + RQ) on return.
+    __device__ __forceinline__ void ensure(uint32_t bitpos) {
+        const uint32_t q0 = bitpos >> 7, need = q0 + RQ;
+        if (fq < need) {
+            if (fq < q0) fq = q0;
+            while (fq < need) { issue(fq); fq++; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads, about
+    // 0.4 on average, so one (predicated) copy per group keeps the ring RQ quads ahead; a lane whose
+    // ring has fallen behind (a run of maximal codes) is sent to the slow path, whose ensure() refills
+    // it.  The group needs quads up to (bitpos >> 7) + 3: with fq >= (bitpos >> 7) + 10 they were
+    // requested at least 6 groups ago, so only copies older than that are waited for.
+    __device__ __forceinline__ bool prefetch_group(uint32_t bitpos) {
+        const uint32_t q0 = bitpos >> 7;
+        if (fq < q0 + RQ) { issue(fq); fq++; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 6;" ::: "memory");
+        return fq >= q0 + 10;
+    }
+    __device__ __forceinline__ void select_channel(uint32_t ch) { column = rows0 + ch * channel_stride; }
+};
+
+template <bool NARROW>
+struct DeviceIOT : DeviceIO {
+    __device__ __forceinline__ void store8(uint32_t t, const int32_t (&e)[8]) {
+        if (NARROW) {
+            uint4 v;
+            v.x = __byte_perm((uint32_t)e[0], (uint32_t)e[1], 0x5410);
+            v.y = __byte_perm((uint32_t)e[2], (uint32_t)e[3], 0x5410);
+            v.z = __byte_perm((uint32_t)e[4], (uint32_t)e[5], 0x5410);
+            v.w = __byte_perm((uint32_t)e[6], (uint32_t)e[7], 0x5410);
+            *reinterpret_cast<uint4*>(column + (uint64_t)t * (SEQ_ROW_BYTES / 8)) = v;
+        } else {
+            char* p = column + (uint64_t)t * (SEQ_ROW_BYTES / 4);
+            *reinterpret_cast<int4*>(p) = make_int4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<int4*>(p + SEQ_ROW_BYTES) = make_int4(e[4], e[5], e[6], e[7]);
+        }
+    }
+    __device__ __forceinline__ void store1(uint32_t t, int32_t e) {
+        if (NARROW) *reinterpret_cast<int16_t*>(column + seq_elem_offset<true>(t)) = (int16_t)e;
+        else *reinterpret_cast<int32_t*>(column + seq_elem_offset<false>(t)) = e;
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// Kernel 1: entropy decode, one lane per frame
+// ---------------------------------------------------------------------------------
+template <bool NARROW>
+__global__ void __launch_bounds__(ENT_SEQ_WARPS * 32)
+entropy_seq_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
+                   uint32_t n_frames, clx_frame_result* __restrict__ results, SeqParams* __restrict__ params,
+                   char* __restrict__ scratch, uint32_t CH, uint32_t rows_per_channel, int* __restrict__ need_generic) {
+    __shared__ __align__(256) uint4 s_ring[ENT_SEQ_WARPS][32][RQ];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * ENT_SEQ_WARPS + warp;
+    const uint32_t fidx = w * 32 + lane;
+    const bool live = fidx < n_frames;
+
+    SeqLane<DeviceIOT<NARROW>, NARROW> L;
+    L.mode = SEQ_DONE; L.ok = true; L.slow_next = false; L.consumed = 0; L.n_left = 0; L.t = 0;
+    L.io.ring = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][lane][0]);
+    L.io.rot = (lane & 7u) << 4;
+    L.io.fq = 0;
+    L.io.wp = 0;
+    L.io.channel_stride = (uint64_t)rows_per_channel * SEQ_ROW_BYTES;
+    L.io.rows0 = scratch + (uint64_t)w * CH * L.io.channel_stride + lane * 16;
+    L.io.column = L.io.rows0;
+    L.io.gbase = reinterpret_cast<const uint4*>(bytes);
+    L.io.qlim = 0;
+    if (live) {
+        const clx_frame_desc d = descs[fidx];
+        const uint64_t aligned = d.byte_offset & ~15ull;
+        L.io.gbase = reinterpret_cast<const uint4*>(bytes + aligned);
+        L.io.qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x1ffffffu);
+        L.init(d, params + (size_t)fidx * CH, CH);
+    }
+    while (__any_sync(0xffffffffu, !L.done())) {
+        if (L.fast_ready()) L.fast_group();
+        else if (!L.done()) L.slow_step();
+        __syncwarp();
+    }
+    if (live) {
+        clx_frame_result res;
+        res.status = L.ok ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
+        res.consumed = L.consumed;
+        results[fidx] = res;
+        if (!L.ok) *need_generic = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Kernel 2: prediction + wasted shift + decorrelation, one lane per subframe
+// ---------------------------------------------------------------------------------
+constexpr int PRE_SEQ_WARPS = 2;
+constexpr int PF_SLOTS = 8;   // prefetch ring: units (8 samples per lane) it holds
+constexpr int PF_DEPTH = 6;   // units in flight
+
+// One trip of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
+// v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first, the terms
+// with fresh samples last, most recent last — the serial chain per sample is one multiply-add,
+// the shift and the residual add.  ACC = long long is the reference's arithmetic verbatim; ACC = int
+// is the same recurrence in wrapping 32-bit arithmetic, bit-identical whenever
+// sum|coef| * max|sample| < 2^31 — which is re-checked against the samples actually produced.
+template <int TAPS, int U, typename ACC>
+__device__ __forceinline__ void seq_trip(int32_t (&v)[TAPS + U], const int32_t (&c)[TAPS], const int32_t* r, uint32_t shift) {
+    ACC part[U];
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+        ACC acc = 0;
+#pragma unroll
+        for (int j = 0; j < TAPS; j++)
+            if (i + TAPS - 1 - j < TAPS) acc += (ACC)c[j] * (ACC)v[i + TAPS - 1 - j];
+        part[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+        ACC acc = part[i];
+#pragma unroll
+        for (int j = TAPS - 1; j >= 0; j--)
+            if (i + TAPS - 1 - j >= TAPS) acc += (ACC)c[j] * (ACC)v[i + TAPS - 1 - j];
+        v[TAPS + i] = (int32_t)(acc >> shift) + r[i];
+    }
+}
+
+// Where the samples of tile rows 2q and 2q+1 go (q = lane >> 1): the two lanes of a pair hold the
+// same record and share the rows' 16-byte vectors between them.  Rows 2q, 2q+1 are neighbouring
+// channels of one frame when the batch has at least two channel slots — then `ca` is the frame's
+// stereo mode if the pair is its (channel 0, channel 1) — and two unrelated mono frames otherwise.
+struct PairRegs {
+    int32_t* out_a;     // row 2q's first output element (nullptr: idle row)
+    int32_t* out_b;     // row 2q+1's
+    uint32_t bs_a, bs_b;
+    uint32_t wasted_a, wasted_b;
+    uint32_t ca;        // 8 left/side, 9 side/right, 10 mid/side, 0 independent
+    bool vec_a, vec_b;  // 16-byte stores allowed
+};
+
+__device__ __forceinline__ uint32_t seq_tile_word(uint32_t row, uint32_t col) {
+    return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+}
+__device__ __forceinline__ void seq_store_vec(int32_t* out, uint32_t bs, bool vec, uint32_t g, const int4& v) {
+    if (out == nullptr || g >= bs) return;
+    if (vec && g + 4 <= bs) *reinterpret_cast<int4*>(out + g) = v;
+    else {
+        out[g] = v.x;
+        if (g + 1 < bs) out[g + 1] = v.y;
+        if (g + 2 < bs) out[g + 2] = v.z;
+        if (g + 3 < bs) out[g + 3] = v.w;
+    }
+}
+__device__ __forceinline__ int4 shl4(const int4& v, uint32_t s) {
+    return make_int4((int32_t)((uint32_t)v.x << s), (int32_t)((uint32_t)v.y << s), (int32_t)((uint32_t)v.z << s),
+                     (int32_t)((uint32_t)v.w << s));
+}
+// mid/side -> left/right (src/frame.rs:371-389).  The reference computes m2 = (mid*2)|(side&1) and
+// (m2 +- side)/2 in wrapping i32; with no wrap (|mid|, |side| < 2^29, checked by the caller against
+// the samples produced) that is mid + (side>>1) + (side&1) and mid - (side>>1), floor shifts.
+__device__ __forceinline__ void mid_side(int32_t& a, int32_t& b) {
+    const int32_t h = b >> 1;
+    const int32_t l = a + h + (b & 1);
+    b = a - h;
+    a = l;
+}
+
+// Writes the warp's 32x32 tile (steps [g0, g0+32) of every lane's subframe) to global memory: wasted
+// bits (src/subframe.rs:216-225), decorrelation (src/frame.rs:319-389), planar i32.  Lane (q, h) takes
+// vectors 2i+h, i = 0..3, of rows 2q and 2q+1: a pair of lanes writes whole 32-byte sectors of both.
+// CHECKED = false is for tiles wholly inside every active row with 16-byte stores allowed everywhere.
+template <bool CHECKED>
+__device__ __forceinline__ void seq_flush(const int32_t* tile, const PairRegs& pr, uint32_t g0, uint32_t lane, bool any_wasted) {
+    __syncwarp();
+    const uint32_t r0 = lane & ~1u, r1 = r0 | 1u, h = lane & 1u;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+        const uint32_t grp = 2 * i + h;
+        const uint32_t g = g0 + grp * 4;
+        int4 a = *reinterpret_cast<const int4*>(tile + r0 * 32 + ((grp ^ (r0 & 7)) << 2));
+        int4 b = *reinterpret_cast<const int4*>(tile + r1 * 32 + ((grp ^ (r1 & 7)) << 2));
+        if (any_wasted) { a = shl4(a, pr.wasted_a); b = shl4(b, pr.wasted_b); }
+        if (pr.ca == 10) {
+            mid_side(a.x, b.x); mid_side(a.y, b.y); mid_side(a.z, b.z); mid_side(a.w, b.w);
+        } else if (pr.ca == 8) {  // left/side (src/frame.rs:319-334)
+            b.x = (int32_t)((uint32_t)a.x - (uint32_t)b.x); b.y = (int32_t)((uint32_t)a.y - (uint32_t)b.y);
+            b.z = (int32_t)((uint32_t)a.z - (uint32_t)b.z); b.w = (int32_t)((uint32_t)a.w - (uint32_t)b.w);
+        } else if (pr.ca == 9) {  // side/right (src/frame.rs:345-360)
+            a.x = (int32_t)((uint32_t)a.x + (uint32_t)b.x); a.y = (int32_t)((uint32_t)a.y + (uint32_t)b.y);
+            a.z = (int32_t)((uint32_t)a.z + (uint32_t)b.z); a.w = (int32_t)((uint32_t)a.w + (uint32_t)b.w);
+        }
+        if (CHECKED) {
+            seq_store_vec(pr.out_a, pr.bs_a, pr.vec_a, g, a);
+            seq_store_vec(pr.out_b, pr.bs_b, pr.vec_b, g, b);
+        } else {
+            if (pr.out_a != nullptr) *reinterpret_cast<int4*>(pr.out_a + g) = a;
+            if (pr.out_b != nullptr) *reinterpret_cast<int4*>(pr.out_b + g) = b;
+        }
+    }
+    __syncwarp();
+}
+
+template <int TAPS, int U, typename ACC, bool NARROW>
+__device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column, uint32_t bs, uint32_t order, uint32_t shift,
+                                                 const SeqParams* __restrict__ sp, bool active, int32_t* tile,
+                                                 const PairRegs& pr, uint4* pf, uint32_t lane, bool all_vec, bool any_wasted,
+                                                 int32_t& smin, int32_t& smax) {
+    int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
+#pragma unroll
+    for (int j = 0; j < TAPS; j++) {
+        c[j] = (active && (uint32_t)j < order) ? (int32_t)sp->coefs[j] : 0;
+        // Opaque to the optimiser: otherwise the i16 -> i64 promotion is folded into a full 64-bit
+        // multiply (3 instructions) instead of one signed 32x32+64 IMAD.WIDE per tap.
+        asm volatile("" : "+r"(c[j]));
+        h[j] = 0;
+    }
+    const uint32_t max_bs = __reduce_max_sync(0xffffffffu, active ? bs : 0u);
+    const uint32_t min_bs = __reduce_min_sync(0xffffffffu, active ? bs : 0xffffffffu);
+    const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
+    const uint32_t head_end = min(max_bs, (max_order + 31u) & ~31u);  // whole tiles
+    const uint32_t bulk_end = min_bs > head_end ? head_end + ((min_bs - head_end) & ~31u) : head_end;
+
+    auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
+        for (uint32_t t = t0; t < t1; t++) {
+            const bool inside = active && t < bs;
+            int32_t val = 0;
+            if (inside) {
+                if (t < order) val = sp->warm[t];
+                else {
+                    const int32_t r = NARROW ? (int32_t)*reinterpret_cast<const int16_t*>(column + seq_elem_offset<true>(t))
+                                             : *reinterpret_cast<const int32_t*>(column + seq_elem_offset<false>(t));
+                    long long acc = 0;
+#pragma unroll
+                    for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
+                    val = r + (sizeof(ACC) == 8 ? (int32_t)(acc >> shift) : (int32_t)((int32_t)acc >> shift));
+                }
+                smin = min(smin, val);
+                smax = max(smax, val);
+            }
+#pragma unroll
+            for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = val;
+            tile[seq_tile_word(lane, t & 31)] = val;
+            if ((t & 31) == 31) seq_flush<true>(tile, pr, t - 31, lane, any_wasted);
+        }
+    };
+    guarded(0, head_end);
+    if (bulk_end > head_end) {
+        int32_t v[TAPS + U];
+#pragma unroll
+        for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
+        // Residual rows stream L2 -> shared memory by cp.async PF_DEPTH units ahead: lane l's 16 bytes of a
+        // row sit next to lane l+CH's, so a warp's copies are a few contiguous runs.  A unit = 8 samples.
+        constexpr int CPS = NARROW ? 1 : 2;  // 16-byte copies per unit
+        const uint32_t pf_s = (uint32_t)__cvta_generic_to_shared(pf) + lane * 16;
+        auto request = [&](uint32_t unit) {
+            const uint32_t t = min(head_end + unit * 8u, bulk_end - 8u);
+#pragma unroll
+            for (int q = 0; q < CPS; q++) {
+                const char* src = column + (uint64_t)(NARROW ? (t >> 3) : (t >> 2) + q) * SEQ_ROW_BYTES;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pf_s + ((unit % PF_SLOTS) * CPS + q) * 512u), "l"(src)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int p = 0; p < PF_DEPTH; p++) request(p);
+        uint32_t unit = 0;
+        for (uint32_t t = head_end; t < bulk_end; t += 8, unit++) {
+            request(unit + PF_DEPTH);
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH) : "memory");
+            int32_t r[8];
+            if (NARROW) {
+                const uint4 x = pf[(unit % PF_SLOTS) * 32 + lane];
+                r[0] = (int32_t)(int16_t)(x.x & 0xffffu); r[1] = (int32_t)x.x >> 16;
+                r[2] = (int32_t)(int16_t)(x.y & 0xffffu); r[3] = (int32_t)x.y >> 16;
+                r[4] = (int32_t)(int16_t)(x.z & 0xffffu); r[5] = (int32_t)x.z >> 16;
+                r[6] = (int32_t)(int16_t)(x.w & 0xffffu); r[7] = (int32_t)x.w >> 16;
+            } else {
+                const uint4 x = pf[((unit % PF_SLOTS) * 2) * 32 + lane], y = pf[((unit % PF_SLOTS) * 2 + 1) * 32 + lane];
+                r[0] = (int32_t)x.x; r[1] = (int32_t)x.y; r[2] = (int32_t)x.z; r[3] = (int32_t)x.w;
+                r[4] = (int32_t)y.x; r[5] = (int32_t)y.y; r[6] = (int32_t)y.z; r[7] = (int32_t)y.w;
+            }
+#pragma unroll
+            for (int half = 0; half < 8 / U; half++) {
+                seq_trip<TAPS, U, ACC>(v, c, r + half * U, shift);
+#pragma unroll
+                for (int i = 0; i < U; i += 2) {
+                    smax = __vimax3_s32(smax, v[TAPS + i], v[TAPS + i + 1]);
+                    smin = __vimin3_s32(smin, v[TAPS + i], v[TAPS + i + 1]);
+                }
+#pragma unroll
+                for (int q = 0; q < U / 4; q++) {
+                    const uint32_t col = (t + half * U + 4 * q) & 31;
+                    *reinterpret_cast<int4*>(tile + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) =
+                        make_int4(v[TAPS + 4 * q], v[TAPS + 4 * q + 1], v[TAPS + 4 * q + 2], v[TAPS + 4 * q + 3]);
+                }
+#pragma unroll
+                for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
+            }
+            if (((t + 8) & 31) == 0) {  // a tile inside [head_end, bulk_end) lies inside every active row
+                if (all_vec) seq_flush<false>(tile, pr, t + 8 - 32, lane, any_wasted);
+                else seq_flush<true>(tile, pr, t + 8 - 32, lane, any_wasted);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the look-ahead copies past the bulk are never used
+    }
+    guarded(bulk_end, max_bs);
+    if (max_bs & 31) seq_flush<true>(tile, pr, max_bs & ~31u, lane, any_wasted);
+}
+
+template <bool NARROW>
+__global__ void __launch_bounds__(PRE_SEQ_WARPS * 32)
+predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, int32_t* __restrict__ out,
+                   clx_frame_result* __restrict__ results, const SeqParams* __restrict__ params,
+                   const char* __restrict__ scratch, uint32_t CH, uint32_t ch_log2, uint32_t rows_per_channel,
+                   uint32_t n_pwarps, int* __restrict__ need_generic) {
+    __shared__ __align__(16) int32_t s_tile[PRE_SEQ_WARPS][32 * 32];
+    __shared__ __align__(16) uint4 s_pf[PRE_SEQ_WARPS][PF_SLOTS * (NARROW ? 1 : 2) * 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pw = blockIdx.x * PRE_SEQ_WARPS + warp;  // CH prediction warps per entropy warp
+    if (pw >= n_pwarps) return;
+    const uint32_t w = pw >> ch_log2, part = pw & (CH - 1);
+    const uint32_t j = part * (32u >> ch_log2) + (lane >> ch_log2);  // frame within the entropy warp
+    const uint32_t c = lane & (CH - 1);
+    const uint32_t f = w * 32 + j;
+    int32_t* tile = s_tile[warp];
+    const char* column = scratch + ((uint64_t)(w * CH + c) * rows_per_channel) * SEQ_ROW_BYTES + j * 16;
+
+    bool active = false, narrow_ok = true;
+    uint32_t bs = 0, order = 0, shift = 0, wasted = 0, ca = 0, absum = 0;
+    const SeqParams* sp = params;
+    int32_t* sub = nullptr;
+    if (f < n_frames && results[f].status == CLX_OK) {
+        const clx_frame_desc d = descs[f];
+        if (c < d.n_channels) {
+            sp = params + (size_t)f * CH + c;
+            active = true;
+            bs = d.block_size;
+            order = (uint32_t)sp->order;
+            shift = (uint32_t)sp->shift;
+            wasted = (uint32_t)sp->wasted;
+            absum = sp->absum;
+            ca = d.channel_assignment >= 8 ? d.channel_assignment : 0u;
+            sub = out + d.out_offset + (size_t)c * bs;
+            uint32_t bits = d.bits_per_sample;  // nominal sample width (one extra bit for a side channel)
+            if (d.channel_assignment == 9) bits += (c == 0);
+            else if (d.channel_assignment == 8 || d.channel_assignment == 10) bits += (c == 1);
+            // valid streams keep |sample| <= 2^(bits-1); anything beyond is caught by the check below
+            narrow_ok = ((unsigned long long)absum << (bits - 1)) < (1ull << 31);
+        }
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
+    // the pair record: this lane's row and its neighbour's (lane ^ 1)
+    const bool vec_own = (reinterpret_cast<uintptr_t>(sub) & 15) == 0;
+    const uint32_t ca_own = c == 0 ? ca : 0u;
+    const unsigned long long sub_other = __shfl_xor_sync(0xffffffffu, (unsigned long long)(uintptr_t)sub, 1);
+    const uint32_t bs_other = __shfl_xor_sync(0xffffffffu, bs, 1);
+    const uint32_t wasted_other = __shfl_xor_sync(0xffffffffu, wasted, 1);
+    const uint32_t ca_other = __shfl_xor_sync(0xffffffffu, ca_own, 1);
+    const bool vec_other = __shfl_xor_sync(0xffffffffu, vec_own ? 1 : 0, 1) != 0;
+    const bool odd = lane & 1u;
+    PairRegs pr;
+    pr.out_a = odd ? reinterpret_cast<int32_t*>((uintptr_t)sub_other) : sub;
+    pr.out_b = odd ? sub : reinterpret_cast<int32_t*>((uintptr_t)sub_other);
+    pr.bs_a = odd ? bs_other : bs;
+    pr.bs_b = odd ? bs : bs_other;
+    pr.wasted_a = odd ? wasted_other : wasted;
+    pr.wasted_b = odd ? wasted : wasted_other;
+    pr.ca = odd ? ca_other : ca_own;
+    pr.vec_a = odd ? vec_other : vec_own;
+    pr.vec_b = odd ? vec_own : vec_other;
+    const bool all_vec = __all_sync(0xffffffffu, !active || vec_own);
+
+    const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
+    const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
+    const bool any_wasted = __any_sync(0xffffffffu, active && wasted != 0);
+    int32_t smin = 0, smax = 0;
+#define CLX_ROWS(T, UU, A) predict_seq_rows<T, UU, A, NARROW>(column, bs, order, shift, sp, active, tile, pr, s_pf[warp], lane, all_vec, any_wasted, smin, smax)
+    if (all_narrow) {
+        if (max_order <= 4) CLX_ROWS(4, 8, int);
+        else if (max_order <= 8) CLX_ROWS(8, 8, int);
+        else if (max_order <= 12) CLX_ROWS(12, 4, int);
+        else CLX_ROWS(32, 4, int);
+    } else {
+        if (max_order <= 4) CLX_ROWS(4, 8, long long);
+        else if (max_order <= 8) CLX_ROWS(8, 8, long long);
+        else if (max_order <= 12) CLX_ROWS(12, 4, long long);
+        else CLX_ROWS(32, 4, long long);
+    }
+#undef CLX_ROWS
+    // The shortcuts taken above are exact only under conditions on the samples actually produced:
+    //  * i32 accumulator: sum|coef| * max|sample| < 2^31;
+    //  * mid/side without the wrapping intermediate: max|sample| << wasted < 2^29 on both channels.
+    // A frame that fails either is re-decoded by the generic kernel (it never happens in a valid stream).
+    const uint32_t m = max((uint32_t)smax, 0u - (uint32_t)smin);
+    bool redo = false;
+    if (active && all_narrow && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) redo = true;
+    if (active && ca == 10 && (((unsigned long long)m) << wasted) >= (1ull << 29)) redo = true;
+    if (redo) {
+        results[f].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
+        *need_generic = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------
+static inline size_t seq_params_bytes(uint32_t n_warps, uint32_t CH) {
+    const size_t b = (size_t)n_warps * 32 * CH * sizeof(SeqParams);
+    return (b + 511) & ~(size_t)511;
+}
+
+size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames) {
+    const uint32_t n_warps = (n_frames + 31) / 32;
+    const uint32_t rows = plan.narrow ? seq_rows_for<true>(plan.max_bs) : seq_rows_for<false>(plan.max_bs);
+    return seq_params_bytes(n_warps, plan.channels) + (size_t)n_warps * plan.channels * rows * SEQ_ROW_BYTES + 512;
+}
+
+cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
+                       int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
+                       const CoopPlan& plan, cudaStream_t stream, int which) {
+    const uint32_t CH = plan.channels;
+    uint32_t ch_log2 = 0;
+    while ((1u << ch_log2) < CH) ch_log2++;
+    const uint32_t n_warps = (n_frames + 31) / 32;
+    const uint32_t rows = plan.narrow ? seq_rows_for<true>(plan.max_bs) : seq_rows_for<false>(plan.max_bs);
+    // 512-byte aligned: cudaMalloc'd base + 512-byte multiples
+    SeqParams* params = reinterpret_cast<SeqParams*>(d_params);
+    char* scratch = reinterpret_cast<char*>(d_params) + seq_params_bytes(n_warps, CH);
+    dim3 g1((n_warps + ENT_SEQ_WARPS - 1) / ENT_SEQ_WARPS), b1(ENT_SEQ_WARPS * 32);
+    const uint32_t n_pwarps = n_warps * CH;
+    dim3 g2((n_pwarps + PRE_SEQ_WARPS - 1) / PRE_SEQ_WARPS), b2(PRE_SEQ_WARPS * 32);
+    if (plan.narrow) {
+        if (which & 1)
+            entropy_seq_kernel<true><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
+                                                            rows, d_need_generic);
+        if (which & 2)
+            predict_seq_kernel<true><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2,
+                                                            rows, n_pwarps, d_need_generic);
+    } else {
+        if (which & 1)
+            entropy_seq_kernel<false><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
+                                                             rows, d_need_generic);
+        if (which & 2)
+            predict_seq_kernel<false><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2,
+                                                             rows, n_pwarps, d_need_generic);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace clx

@@ -61,6 +61,24 @@ CLX_HD uint32_t hd_clz(uint32_t v) {
     return v ? (uint32_t)__builtin_clz(v) : 32u;
 #endif
 }
+CLX_HD uint32_t hd_msb(uint32_t v) {  // index of the most significant set bit (v != 0)
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    return 31u - (uint32_t)__builtin_clz(v | 1u);
+#endif
+}
+CLX_HD uint32_t hd_neg_lsb(uint32_t u) {  // 0 - (u & 1)
+#ifdef __CUDA_ARCH__
+    int32_t r;
+    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(r) : "r"(u));
+    return (uint32_t)r;
+#else
+    return 0u - (u & 1u);
+#endif
+}
 // upper 32 bits of (hi:lo) << (n & 31)
 CLX_HD uint32_t hd_fsl(uint32_t hi, uint32_t lo, uint32_t n) {
 #ifdef __CUDA_ARCH__
@@ -79,7 +97,8 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 // IO policy (see DeviceIO in clx_seq.cu and HostIO in tools/seq_host.cpp):
 //   uint32_t word(uint32_t wi)            big-endian word `wi` of the frame (relative to its 16-byte aligned base)
 //   void ensure(uint32_t bitpos)          the next 2048 bits from bitpos are readable through word()
-//   void prefetch_group(uint32_t bitpos)  steady-state refill, called once per fast group
+//   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: take the slow path
+//   void seek_next(uint32_t wi), uint32_t next_word()   sequential word reads (the register window's refill)
 //   void select_channel(uint32_t ch)      subsequent stores go to channel ch's rows
 //   void store8(uint32_t t, const int32_t (&e)[8])   residuals t..t+7, t % 8 == 0
 //   void store1(uint32_t t, int32_t e)
@@ -91,7 +110,7 @@ struct SeqLane {
     uint32_t o;           // bit cursor, relative to the frame's 16-byte aligned base
     uint32_t W0, W1, W2;  // big-endian words o>>5, +1, +2 (maintained while mode == SEQ_RUN)
     uint32_t mode, ch, t, n_left, parts_left, per, order, pbits;
-    uint32_t k, K, c31k, thr;
+    uint32_t k, K, Kneg, K30, c32k, thr;
     uint32_t consumed;
     bool ok, slow_next, first_part;
 
@@ -104,7 +123,7 @@ struct SeqLane {
         o = bit0 + (uint32_t)d.header_len * 8;
         W0 = W1 = W2 = 0;
         mode = SEQ_SUBFRAME; ch = 0; t = 0; n_left = 0; parts_left = 0; per = 0; order = 0; pbits = 4;
-        k = 0; K = 1; c31k = 31; thr = 1;
+        k = 0; K = 1; Kneg = 0xffffffffu; K30 = 30; c32k = 32; thr = 1;
         consumed = 0;
         ok = true; slow_next = false; first_part = false;
         if (nch > max_channels || fbps == 0 || (NARROW && fbps > 16)) fail();
@@ -118,6 +137,7 @@ struct SeqLane {
     CLX_HD void window_seek() {
         const uint32_t wi = o >> 5;
         W0 = io.word(wi); W1 = io.word(wi + 1); W2 = io.word(wi + 2);
+        io.seek_next(wi + 3);
     }
     CLX_HD void emit1(int32_t e) {  // one residual through the slow path
         if (NARROW && (e < -32768 || e > 32767)) { fail(); return; }
@@ -135,34 +155,35 @@ struct SeqLane {
     // ---- eight Rice codes (src/subframe.rs:336-348) ----
     // Precondition fast_ready().  A code is taken here when it fits the 32-bit window `hi`
     // (unary + terminator + k bits <= 32) and, for the narrow scratch, its value fits 16 bits: both
-    // are the single comparison hi >= thr.  Anything else ends the group early; the slow path takes
-    // that one code.
+    // are the single comparison hi >= thr.  The eight codes are decoded straight through; if any of
+    // them failed the comparison, what came after it is meaningless (but harmless: nothing is
+    // stored, and every shared-memory address is masked into the lane's ring), the cursor is put
+    // back and the slow path takes the codes one by one until the next group boundary.
     CLX_HD void fast_group() {
-        io.prefetch_group(o);
+        if (!io.prefetch_group(o)) { slow_next = true; return; }  // ring not far enough ahead: the slow path refills it
+        const uint32_t o0 = o;
         int32_t e[8];
-        uint32_t cnt = 8;
+        bool bad = false;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t hi = hd_fsl(W0, W1, o);
-            if (hi < thr) { cnt = (uint32_t)i; break; }
-            const uint32_t q = hd_clz(hi);        // unary quotient = zeros before the terminator
-            const uint32_t x = hi << q;           // terminator at bit 31, remainder below it
-            const uint32_t v = x >> c31k;         // K + r
-            const uint32_t u = q * K + v - K;     // (q << k) | r
-            e[i] = (int32_t)((u >> 1) ^ (0u - (u & 1u)));  // rice_to_signed, src/subframe.rs:157-170
-            const uint32_t on = o + q + 1 + k;
-            if ((on ^ o) >> 5) { W0 = W1; W1 = W2; W2 = io.word((on >> 5) + 2); }
+            bad = bad || hi < thr;
+            const uint32_t m = hd_msb(hi);        // terminator at bit m: unary quotient q = 31 - m
+            const uint32_t v = hi >> ((m - k) & 31u);  // K + r
+            const uint32_t u = m * Kneg + (v + K30);  // (q << k) | r = (30 - m) * K + v
+            e[i] = (int32_t)((u >> 1) ^ hd_neg_lsb(u));  // rice_to_signed, src/subframe.rs:157-170
+            const uint32_t on = o + c32k - m;     // o + q + 1 + k
+            if ((on ^ o) >> 5) { W0 = W1; W1 = W2; W2 = io.next_word(); }
             o = on;
         }
-        if (cnt == 8) io.store8(t, e);
-        else {
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if ((uint32_t)j < cnt) io.store1(t + (uint32_t)j, e[j]);
+        if (bad) {
+            o = o0;  // the slow path re-reads the window (and re-seeds the sequential reads) after its code
             slow_next = true;
+            return;
         }
-        t += cnt;
-        n_left -= cnt;
+        io.store8(t, e);
+        t += 8;
+        n_left -= 8;
         if (n_left == 0) advance();
     }
 
@@ -201,7 +222,9 @@ struct SeqLane {
         first_part = false;
         parts_left--;
         K = 1u << k;
-        c31k = 31u - k;
+        K30 = 30u * K;
+        Kneg = 0u - K;
+        c32k = 32u + k;
         // fast-path bound on the unary quotient q: q + 1 + k <= 32, and (narrow) (q + 1) << k <= 65536
         uint32_t qmax = 31u - k;
         if (NARROW) {

@@ -20,10 +20,11 @@ def golden():
     return np.load(path, allow_pickle=False)
 
 
-@pytest.fixture(scope="session", params=["coop", "generic"])
+@pytest.fixture(scope="session", params=["seq", "warp", "generic"])
 def ctx(request):
-    """Both device paths: the cooperative fast path (with its fallback) and the generic kernel alone."""
+    """Every device path: the fast path (lane-per-frame entropy + lane-per-subframe prediction, with its
+    fallback), the earlier warp-per-frame fast path, and the generic kernel alone."""
     import claxon_b200 as cb
-    c = cb.Context(device=0, generic_only=(request.param == "generic"))
+    c = cb.Context(device=0, generic_only=(request.param == "generic"), warp_per_frame=(request.param == "warp"))
     yield c
     c.close()

@@ -27,8 +27,11 @@ struct HostIO {
         }
         return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
     }
+    uint32_t wnext = 0;
+    void seek_next(uint32_t wi) { wnext = wi; }
+    uint32_t next_word() { return word(wnext++); }
     void ensure(uint32_t) {}
-    void prefetch_group(uint32_t) {}
+    bool prefetch_group(uint32_t) { return true; }
     void select_channel(uint32_t ch) { column = frame_rows + ch * channel_stride; }
     void store1(uint32_t t, int32_t e) {
         if (narrow) { int16_t v = (int16_t)e; memcpy(column + clx::seq_elem_offset<true>(t), &v, 2); }
