@@ -148,15 +148,15 @@ def main():
     ap.add_argument("--impl", default="claxon_b200", choices=["claxon_b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--frames", type=int, default=None, help="override frames per batch")
-    ap.add_argument("--inflight", type=int, default=32, help="distinct device-resident batches cycled")
-    ap.add_argument("--streams", type=int, default=32)
+    ap.add_argument("--inflight", type=int, default=64, help="distinct device-resident batches cycled")
+    ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     # more hardware work queues than the default 8, so that the batches in flight really overlap
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "64")
     from claxon_b200 import synth
 
     cfg = synth.workload_config(args.workload, args.frames)

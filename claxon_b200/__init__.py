@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, OPT_WARP_PER_FRAME,
+from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, OPT_WARP_PER_FRAME, OPT_LANE_PER_FRAME,
                    FRAME_VARIABLE_BLOCKING,
                    FRAME_CRC16_VERIFIED)
 
@@ -166,12 +166,14 @@ class Context:
     """clx_ctx: one per host thread / GPU. Raises Error(NO_DEVICE) without a usable GPU."""
 
     def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False,
-                 warp_per_frame: bool = False):
-        """`generic_only` / `warp_per_frame` select the other device paths (testing, A/B measurements); the
-        default is the lane-per-frame entropy kernel + lane-per-subframe prediction kernel (csrc/clx_seq.cu)."""
+                 warp_per_frame: bool = False, lane_per_frame: bool = False):
+        """Default: device-resident batches and large calls use the lane-per-frame entropy kernel + lane-per-
+        subframe prediction kernel (csrc/clx_seq.cu); small synchronous host-buffer calls (latency regime) use the
+        warp-per-frame path (csrc/clx_coop.cu).  `warp_per_frame` / `lane_per_frame` force one of them everywhere,
+        `generic_only` bypasses both (testing, A/B measurements)."""
         self._L = _lib.load()
         flags = ((0 if verify_crc else OPT_NO_VERIFY_CRC) | (OPT_GENERIC_KERNEL_ONLY if generic_only else 0)
-                 | (OPT_WARP_PER_FRAME if warp_per_frame else 0))
+                 | (OPT_WARP_PER_FRAME if warp_per_frame else 0) | (OPT_LANE_PER_FRAME if lane_per_frame else 0))
         opts = _lib.Options(device, flags, n_streams, 0)
         h = C.c_void_p()
         _check(self._L.clx_ctx_create(C.byref(opts), C.byref(h)))

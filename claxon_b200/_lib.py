@@ -44,6 +44,7 @@ assert C.sizeof(FrameDesc) == 40 and C.sizeof(FrameResult) == 8
 OPT_NO_VERIFY_CRC = 1
 OPT_GENERIC_KERNEL_ONLY = 2
 OPT_WARP_PER_FRAME = 4
+OPT_LANE_PER_FRAME = 8
 FRAME_VARIABLE_BLOCKING = 1
 FRAME_CRC16_VERIFIED = 2
 

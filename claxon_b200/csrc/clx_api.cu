@@ -28,7 +28,8 @@ struct clx_ctx {
     int sm_count = 148;
     size_t smem_budget = 227 * 1024;
     bool use_coop = true;
-    bool warp_per_frame = false;  // CLX_OPT_WARP_PER_FRAME: the earlier fast path (clx_coop.cu) instead of clx_seq.cu
+    bool warp_per_frame = false;  // CLX_OPT_WARP_PER_FRAME: the warp-per-frame fast path (clx_coop.cu) everywhere
+    bool lane_per_frame_always = false;  // CLX_OPT_LANE_PER_FRAME: clx_seq.cu even for small synchronous calls
     // grow-only device scratch for clx_decode_frames, one set per stream (chunk pipelining)
     struct Scratch {
         uint8_t* d_bytes = nullptr; size_t bytes_cap = 0;
@@ -58,6 +59,11 @@ struct clx_batch {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaStream_t last_stream = nullptr;
     clx::CoopPlan plan;
+    // The batch's launch sequence (flag reset + kernels) captured once as a CUDA graph: a decode is then
+    // one graph launch instead of five stream operations, which matters when a step is ~25 us.
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_launches = 0;   // kernel launches inside the graph
+    bool graph_failed = false;
 };
 
 namespace {
@@ -130,7 +136,14 @@ void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, 
 }
 
 // Chooses how a set of frames maps onto the cooperative kernel (frames per CTA, shared memory).
-clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t n) {
+// Two fast paths, two regimes.  The lane-per-frame path (clx_seq.cu) has the fewest instructions per
+// sample and is what a stream of batches should use; but a lane walks its whole frame alone, so one call
+// takes ~0.4 ms of device time however few frames it holds.  A synchronous host-buffer call with a few
+// thousand frames and nothing else in flight is latency-bound: there the warp-per-frame path
+// (clx_coop.cu: 32 lanes share a frame, ~0.25 ms per 1024 frames) finishes sooner and lets the PCM
+// copy-out start earlier.  `latency_call` = the plan is for such a call.
+constexpr size_t kLatencyRegimeFrames = 4096;
+clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t n, bool latency_call = false) {
     clx::CoopPlan plan;
     if (!ctx->use_coop) return plan;
     uint32_t max_elems = 0, max_ch = 0, max_bs = 0, max_bps = 0;
@@ -140,7 +153,8 @@ clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t 
         max_bs = std::max<uint32_t>(max_bs, descs[i].block_size);
         max_bps = std::max<uint32_t>(max_bps, descs[i].bits_per_sample);
     }
-    if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame) {
+    if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame &&
+        !(latency_call && !ctx->lane_per_frame_always)) {
         plan.G = 2;
         plan.narrow = max_bps <= 16 ? 1u : 0u;
         plan.max_bs = max_bs;
@@ -178,6 +192,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
     }
     if (opts && (opts->flags & CLX_OPT_GENERIC_KERNEL_ONLY)) ctx->use_coop = false;
     if (opts && (opts->flags & CLX_OPT_WARP_PER_FRAME)) ctx->warp_per_frame = true;
+    if (opts && (opts->flags & CLX_OPT_LANE_PER_FRAME)) ctx->lane_per_frame_always = true;
     ctx->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     *out = ctx;
     return CLX_OK;
@@ -267,7 +282,7 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc),
                                 cudaMemcpyHostToDevice, st));
-        const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf);
+        const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf, n_frames <= kLatencyRegimeFrames);
         if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return rc;
         CU(ctx, clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
                                    sc.d_need_hi, sc.d_params, plan, st, &ctx->launches));
@@ -330,13 +345,46 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     return CLX_OK;
 }
 
+namespace {
+// Enqueues one decode of a device-resident batch on `st`, through the batch's graph when possible.
+int enqueue_batch(clx_ctx* ctx, clx_batch* b, cudaStream_t st) {
+    static const bool no_graph = getenv("CLX_NO_GRAPH") != nullptr;
+    if (!no_graph && !b->graph && !b->graph_failed && b->n_frames > 0) {
+        cudaGraph_t g = nullptr;
+        uint64_t n = 0;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            cudaError_t e1 = clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
+                                                b->d_need_hi, b->d_params, b->plan, st, &n);
+            e = cudaStreamEndCapture(st, &g);
+            if (e1 != cudaSuccess) e = e1;
+        }
+        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&b->graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || !b->graph) {
+            b->graph = nullptr;
+            b->graph_failed = true;
+            cudaGetLastError();
+        } else b->graph_launches = n;
+    }
+    if (b->graph) {
+        CU(ctx, cudaGraphLaunch(b->graph, st));
+        ctx->launches += b->graph_launches;
+        return CLX_OK;
+    }
+    CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
+                               b->d_params, b->plan, st, &ctx->launches));
+    return CLX_OK;
+}
+}  // namespace
+
 int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index) {
     if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
     cudaStream_t st = ctx->streams[stream_index % ctx->streams.size()];
     b->last_stream = st;
     CU(ctx, cudaEventRecord(b->ev_start, st));
-    CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
-                               b->d_params, b->plan, st, &ctx->launches));
+    int rc = enqueue_batch(ctx, b, st);
+    if (rc) return rc;
     CU(ctx, cudaEventRecord(b->ev_stop, st));
     return CLX_OK;
 }
@@ -368,6 +416,7 @@ void clx_batch_destroy(clx_ctx* ctx, clx_batch* b) {
     if (!b) return;
     cudaFree(b->d_bytes); cudaFree(b->d_descs); cudaFree(b->d_out); cudaFree(b->d_results); cudaFree(b->d_need_hi);
     cudaFree(b->d_params);
+    if (b->graph) cudaGraphExecDestroy(b->graph);
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     delete b;
@@ -393,8 +442,8 @@ int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint3
         clx_batch* b = batches[i % n_batches];
         cudaStream_t st = ctx->streams[i % n_streams];
         b->last_stream = st;
-        CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
-                                   b->d_need_hi, b->d_params, b->plan, st, &ctx->launches));
+        int rc = enqueue_batch(ctx, b, st);
+        if (rc) return rc;
     }
     for (uint32_t s = 1; s < n_streams; s++) {
         CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "claxon_b200.h"
 #include "clx_internal.h"
 #include "clx_seq_lane.h"
@@ -31,6 +33,10 @@ namespace clx {
 // ---------------------------------------------------------------------------------
 // Device IO policy of the entropy lane
 // ---------------------------------------------------------------------------------
+// Measurement hook (tools/exp_*.py): bit 0 = the entropy kernel drops its scratch stores, bit 1 = the
+// prediction kernel drops its PCM stores.  Zero in the product; read once per kernel.
+__device__ int g_seq_debug = 0;
+
 constexpr uint32_t RQ = 16;           // ring: quads (16 bytes) per lane
 constexpr int ENT_SEQ_WARPS = 1;      // warps (of 32 frames) per CTA
 
@@ -44,6 +50,7 @@ struct DeviceIO {
     char* rows0;          // channel 0's rows + lane * 16
     char* column;         // current channel's column
     uint64_t channel_stride;
+    bool drop_stores;     // measurement hook
 
     __device__ __forceinline__ void issue(uint32_t q) {
         const uint32_t dst = ring | (((q << 4) + rot) & 0xF0u);
@@ -58,11 +65,11 @@ struct DeviceIO {
         return __byte_perm(v, 0, 0x0123);
     }
     __device__ __forceinline__ void seek_next(uint32_t wi) { wp = (wi << 2) + rot; }
-    __device__ __forceinline__ uint32_t next_word() {
+    __device__ __forceinline__ uint32_t next_raw() {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (wp & 0xFCu)) : "memory");
         wp += 4;
-        return __byte_perm(v, 0, 0x0123);
+        return v;
     }
     // Random access (headers, slow codes): the ring covers quads [bitpos >> 7, (bitpos >> 7) + RQ) on return.
     __device__ __forceinline__ void ensure(uint32_t bitpos) {
@@ -92,6 +99,7 @@ struct DeviceIO {
 template <bool NARROW>
 struct DeviceIOT : DeviceIO {
     __device__ __forceinline__ void store8(uint32_t t, const int32_t (&e)[8]) {
+        if (drop_stores) return;
         if (NARROW) {
             uint4 v;
             v.x = __byte_perm((uint32_t)e[0], (uint32_t)e[1], 0x5410);
@@ -131,6 +139,7 @@ entropy_seq_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const 
     L.io.rot = (lane & 7u) << 4;
     L.io.fq = 0;
     L.io.wp = 0;
+    L.io.drop_stores = (g_seq_debug & 1) != 0;
     L.io.channel_stride = (uint64_t)rows_per_channel * SEQ_ROW_BYTES;
     L.io.rows0 = scratch + (uint64_t)w * CH * L.io.channel_stride + lane * 16;
     L.io.column = L.io.rows0;
@@ -191,17 +200,15 @@ __device__ __forceinline__ void seq_trip(int32_t (&v)[TAPS + U], const int32_t (
     }
 }
 
-// Where the samples of tile rows 2q and 2q+1 go (q = lane >> 1): the two lanes of a pair hold the
-// same record and share the rows' 16-byte vectors between them.  Rows 2q, 2q+1 are neighbouring
-// channels of one frame when the batch has at least two channel slots — then `ca` is the frame's
-// stereo mode if the pair is its (channel 0, channel 1) — and two unrelated mono frames otherwise.
-struct PairRegs {
-    int32_t* out_a;     // row 2q's first output element (nullptr: idle row)
-    int32_t* out_b;     // row 2q+1's
-    uint32_t bs_a, bs_b;
-    uint32_t wasted_a, wasted_b;
-    uint32_t ca;        // 8 left/side, 9 side/right, 10 mid/side, 0 independent
-    bool vec_a, vec_b;  // 16-byte stores allowed
+// Where the samples of a tile row (= a lane = a subframe) go; shared memory, one per lane.  Rows 2p and 2p+1
+// are neighbouring channels of one frame when the batch has at least two channel slots — `ca` on the even
+// row is then the frame's stereo mode if the pair is its (channel 0, channel 1) — and two unrelated mono
+// frames otherwise.
+struct __align__(16) SeqRow {
+    int32_t* out;   // subframe's first output element (nullptr: idle row)
+    uint32_t bs;    // block size
+    uint32_t meta;  // bit 0: 16-byte stores allowed; bits 8-15: wasted bits; bits 16-19 (even rows): 8 left/side,
+                    // 9 side/right, 10 mid/side, 0 independent
 };
 
 __device__ __forceinline__ uint32_t seq_tile_word(uint32_t row, uint32_t col) {
@@ -231,45 +238,51 @@ __device__ __forceinline__ void mid_side(int32_t& a, int32_t& b) {
     a = l;
 }
 
-// Writes the warp's 32x32 tile (steps [g0, g0+32) of every lane's subframe) to global memory: wasted
-// bits (src/subframe.rs:216-225), decorrelation (src/frame.rs:319-389), planar i32.  Lane (q, h) takes
-// vectors 2i+h, i = 0..3, of rows 2q and 2q+1: a pair of lanes writes whole 32-byte sectors of both.
+// Writes a quarter of the warp's 32x32 tile (steps [g0, g0+32) of rows 8q .. 8q+7) to global memory: wasted
+// bits (src/subframe.rs:216-225), decorrelation (src/frame.rs:319-389), planar i32.  Eight lanes take the eight
+// 16-byte vectors of a row pair (rows 2p, 2p+1), so each store instruction of the warp covers four whole
+// 128-byte lines — scattering the lanes over more rows costs the load/store unit a wavefront per line.
 // CHECKED = false is for tiles wholly inside every active row with 16-byte stores allowed everywhere.
 template <bool CHECKED>
-__device__ __forceinline__ void seq_flush(const int32_t* tile, const PairRegs& pr, uint32_t g0, uint32_t lane, bool any_wasted) {
-    __syncwarp();
-    const uint32_t r0 = lane & ~1u, r1 = r0 | 1u, h = lane & 1u;
-#pragma unroll
-    for (uint32_t i = 0; i < 4; i++) {
-        const uint32_t grp = 2 * i + h;
-        const uint32_t g = g0 + grp * 4;
-        int4 a = *reinterpret_cast<const int4*>(tile + r0 * 32 + ((grp ^ (r0 & 7)) << 2));
-        int4 b = *reinterpret_cast<const int4*>(tile + r1 * 32 + ((grp ^ (r1 & 7)) << 2));
-        if (any_wasted) { a = shl4(a, pr.wasted_a); b = shl4(b, pr.wasted_b); }
-        if (pr.ca == 10) {
-            mid_side(a.x, b.x); mid_side(a.y, b.y); mid_side(a.z, b.z); mid_side(a.w, b.w);
-        } else if (pr.ca == 8) {  // left/side (src/frame.rs:319-334)
-            b.x = (int32_t)((uint32_t)a.x - (uint32_t)b.x); b.y = (int32_t)((uint32_t)a.y - (uint32_t)b.y);
-            b.z = (int32_t)((uint32_t)a.z - (uint32_t)b.z); b.w = (int32_t)((uint32_t)a.w - (uint32_t)b.w);
-        } else if (pr.ca == 9) {  // side/right (src/frame.rs:345-360)
-            a.x = (int32_t)((uint32_t)a.x + (uint32_t)b.x); a.y = (int32_t)((uint32_t)a.y + (uint32_t)b.y);
-            a.z = (int32_t)((uint32_t)a.z + (uint32_t)b.z); a.w = (int32_t)((uint32_t)a.w + (uint32_t)b.w);
-        }
-        if (CHECKED) {
-            seq_store_vec(pr.out_a, pr.bs_a, pr.vec_a, g, a);
-            seq_store_vec(pr.out_b, pr.bs_b, pr.vec_b, g, b);
-        } else {
-            if (pr.out_a != nullptr) *reinterpret_cast<int4*>(pr.out_a + g) = a;
-            if (pr.out_b != nullptr) *reinterpret_cast<int4*>(pr.out_b + g) = b;
-        }
+__device__ __forceinline__ void seq_flush_quarter(const int32_t* tile, const SeqRow* rows, uint32_t g0, uint32_t q, uint32_t lane,
+                                                  bool any_wasted) {
+    const uint32_t grp = lane & 7;
+    const uint32_t r0 = (4 * q + (lane >> 3)) * 2, r1 = r0 + 1;
+    const uint32_t g = g0 + grp * 4;
+    const SeqRow i0 = rows[r0], i1 = rows[r1];
+    int4 a = *reinterpret_cast<const int4*>(tile + r0 * 32 + ((grp ^ (r0 & 7)) << 2));
+    int4 b = *reinterpret_cast<const int4*>(tile + r1 * 32 + ((grp ^ (r1 & 7)) << 2));
+    if (any_wasted) { a = shl4(a, (i0.meta >> 8) & 0xffu); b = shl4(b, (i1.meta >> 8) & 0xffu); }
+    const uint32_t ca = (i0.meta >> 16) & 15u;
+    if (ca == 10) {
+        mid_side(a.x, b.x); mid_side(a.y, b.y); mid_side(a.z, b.z); mid_side(a.w, b.w);
+    } else if (ca == 8) {  // left/side (src/frame.rs:319-334)
+        b.x = (int32_t)((uint32_t)a.x - (uint32_t)b.x); b.y = (int32_t)((uint32_t)a.y - (uint32_t)b.y);
+        b.z = (int32_t)((uint32_t)a.z - (uint32_t)b.z); b.w = (int32_t)((uint32_t)a.w - (uint32_t)b.w);
+    } else if (ca == 9) {  // side/right (src/frame.rs:345-360)
+        a.x = (int32_t)((uint32_t)a.x + (uint32_t)b.x); a.y = (int32_t)((uint32_t)a.y + (uint32_t)b.y);
+        a.z = (int32_t)((uint32_t)a.z + (uint32_t)b.z); a.w = (int32_t)((uint32_t)a.w + (uint32_t)b.w);
     }
+    if (CHECKED) {
+        seq_store_vec(i0.out, i0.bs, (i0.meta & 1u) != 0, g, a);
+        seq_store_vec(i1.out, i1.bs, (i1.meta & 1u) != 0, g, b);
+    } else {
+        if (i0.out != nullptr) *reinterpret_cast<int4*>(i0.out + g) = a;
+        if (i1.out != nullptr) *reinterpret_cast<int4*>(i1.out + g) = b;
+    }
+}
+template <bool CHECKED>
+__device__ __forceinline__ void seq_flush(const int32_t* tile, const SeqRow* rows, uint32_t g0, uint32_t lane, bool any_wasted) {
+    __syncwarp();
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) seq_flush_quarter<CHECKED>(tile, rows, g0, i, lane, any_wasted);
     __syncwarp();
 }
 
 template <int TAPS, int U, typename ACC, bool NARROW>
 __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column, uint32_t bs, uint32_t order, uint32_t shift,
                                                  const SeqParams* __restrict__ sp, bool active, int32_t* tile,
-                                                 const PairRegs& pr, uint4* pf, uint32_t lane, bool all_vec, bool any_wasted,
+                                                 const SeqRow* pr, uint4* pf, uint32_t lane, bool all_vec, bool any_wasted,
                                                  int32_t& smin, int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
@@ -331,19 +344,31 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
         };
 #pragma unroll
         for (int p = 0; p < PF_DEPTH; p++) request(p);
+        auto fetch = [&](uint32_t unit, uint4& x, uint4& y) {  // the unit's residuals, shared memory -> registers
+            if (NARROW) x = pf[(unit % PF_SLOTS) * 32 + lane];
+            else { x = pf[((unit % PF_SLOTS) * 2) * 32 + lane]; y = pf[((unit % PF_SLOTS) * 2 + 1) * 32 + lane]; }
+        };
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH - 1) : "memory");
+        uint4 x, y = make_uint4(0, 0, 0, 0), xn, yn = make_uint4(0, 0, 0, 0);
+        fetch(0, x, y);
+        // Samples are staged in one of two 32x32 tiles; while a tile fills (four trips of 8 samples), the
+        // previous one is written out a quarter per trip, so that its shared-memory loads, the
+        // decorrelation and its global stores interleave with the multiply-adds of the recurrence.
+        int32_t* fill = tile;
+        int32_t* drain = tile + 32 * 32;
+        bool have_drain = false;
         uint32_t unit = 0;
         for (uint32_t t = head_end; t < bulk_end; t += 8, unit++) {
             request(unit + PF_DEPTH);
-            asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH) : "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH - 1) : "memory");  // unit + 1 has landed
+            fetch(unit + 1, xn, yn);  // used by the next trip: its latency hides behind this one
             int32_t r[8];
             if (NARROW) {
-                const uint4 x = pf[(unit % PF_SLOTS) * 32 + lane];
                 r[0] = (int32_t)(int16_t)(x.x & 0xffffu); r[1] = (int32_t)x.x >> 16;
                 r[2] = (int32_t)(int16_t)(x.y & 0xffffu); r[3] = (int32_t)x.y >> 16;
                 r[4] = (int32_t)(int16_t)(x.z & 0xffffu); r[5] = (int32_t)x.z >> 16;
                 r[6] = (int32_t)(int16_t)(x.w & 0xffffu); r[7] = (int32_t)x.w >> 16;
             } else {
-                const uint4 x = pf[((unit % PF_SLOTS) * 2) * 32 + lane], y = pf[((unit % PF_SLOTS) * 2 + 1) * 32 + lane];
                 r[0] = (int32_t)x.x; r[1] = (int32_t)x.y; r[2] = (int32_t)x.z; r[3] = (int32_t)x.w;
                 r[4] = (int32_t)y.x; r[5] = (int32_t)y.y; r[6] = (int32_t)y.z; r[7] = (int32_t)y.w;
             }
@@ -358,17 +383,32 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
 #pragma unroll
                 for (int q = 0; q < U / 4; q++) {
                     const uint32_t col = (t + half * U + 4 * q) & 31;
-                    *reinterpret_cast<int4*>(tile + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) =
+                    *reinterpret_cast<int4*>(fill + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) =
                         make_int4(v[TAPS + 4 * q], v[TAPS + 4 * q + 1], v[TAPS + 4 * q + 2], v[TAPS + 4 * q + 3]);
                 }
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
             }
-            if (((t + 8) & 31) == 0) {  // a tile inside [head_end, bulk_end) lies inside every active row
-                if (all_vec) seq_flush<false>(tile, pr, t + 8 - 32, lane, any_wasted);
-                else seq_flush<true>(tile, pr, t + 8 - 32, lane, any_wasted);
+            if (have_drain) {  // a tile inside [head_end, bulk_end) lies inside every active row
+                const uint32_t g0 = (t & ~31u) - 32, quarter = (t >> 3) & 3;
+                if (all_vec) seq_flush_quarter<false>(drain, pr, g0, quarter, lane, any_wasted);
+                else seq_flush_quarter<true>(drain, pr, g0, quarter, lane, any_wasted);
+            }
+            if (((t + 8) & 31) == 0) {  // the tile is full: it becomes the one to write out
+                __syncwarp();
+                int32_t* tmp = fill; fill = drain; drain = tmp;
+                have_drain = true;
+            }
+            x = xn; y = yn;
+        }
+        if (have_drain) {  // the last tile
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                if (all_vec) seq_flush_quarter<false>(drain, pr, bulk_end - 32, i, lane, any_wasted);
+                else seq_flush_quarter<true>(drain, pr, bulk_end - 32, i, lane, any_wasted);
             }
         }
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
         asm volatile("cp.async.wait_group 0;" ::: "memory");  // the look-ahead copies past the bulk are never used
@@ -377,13 +417,18 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
     if (max_bs & 31) seq_flush<true>(tile, pr, max_bs & ~31u, lane, any_wasted);
 }
 
-template <bool NARROW>
+// One instance per order class (CLASS 0: max order of the warp <= 4, 1: <= 8, 2: <= 12, 3: <= 32), launched
+// back to back: a warp does its work in the instance of its class and leaves the others at once.  The
+// 8-tap instance then needs 80 registers instead of the 128 of the 32-tap one, i.e. half as many again
+// resident warps — which is what bounds this latency-chained kernel.
+template <bool NARROW, int CLASS>
 __global__ void __launch_bounds__(PRE_SEQ_WARPS * 32)
 predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, int32_t* __restrict__ out,
                    clx_frame_result* __restrict__ results, const SeqParams* __restrict__ params,
                    const char* __restrict__ scratch, uint32_t CH, uint32_t ch_log2, uint32_t rows_per_channel,
                    uint32_t n_pwarps, int* __restrict__ need_generic) {
-    __shared__ __align__(16) int32_t s_tile[PRE_SEQ_WARPS][32 * 32];
+    __shared__ __align__(16) int32_t s_tile[PRE_SEQ_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
+    __shared__ SeqRow s_rows[PRE_SEQ_WARPS][32];
     __shared__ __align__(16) uint4 s_pf[PRE_SEQ_WARPS][PF_SLOTS * (NARROW ? 1 : 2) * 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t pw = blockIdx.x * PRE_SEQ_WARPS + warp;  // CH prediction warps per entropy warp
@@ -419,43 +464,29 @@ predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, 
         }
     }
     if (!__any_sync(0xffffffffu, active)) return;
-    // the pair record: this lane's row and its neighbour's (lane ^ 1)
-    const bool vec_own = (reinterpret_cast<uintptr_t>(sub) & 15) == 0;
-    const uint32_t ca_own = c == 0 ? ca : 0u;
-    const unsigned long long sub_other = __shfl_xor_sync(0xffffffffu, (unsigned long long)(uintptr_t)sub, 1);
-    const uint32_t bs_other = __shfl_xor_sync(0xffffffffu, bs, 1);
-    const uint32_t wasted_other = __shfl_xor_sync(0xffffffffu, wasted, 1);
-    const uint32_t ca_other = __shfl_xor_sync(0xffffffffu, ca_own, 1);
-    const bool vec_other = __shfl_xor_sync(0xffffffffu, vec_own ? 1 : 0, 1) != 0;
-    const bool odd = lane & 1u;
-    PairRegs pr;
-    pr.out_a = odd ? reinterpret_cast<int32_t*>((uintptr_t)sub_other) : sub;
-    pr.out_b = odd ? sub : reinterpret_cast<int32_t*>((uintptr_t)sub_other);
-    pr.bs_a = odd ? bs_other : bs;
-    pr.bs_b = odd ? bs : bs_other;
-    pr.wasted_a = odd ? wasted_other : wasted;
-    pr.wasted_b = odd ? wasted : wasted_other;
-    pr.ca = odd ? ca_other : ca_own;
-    pr.vec_a = odd ? vec_other : vec_own;
-    pr.vec_b = odd ? vec_own : vec_other;
-    const bool all_vec = __all_sync(0xffffffffu, !active || vec_own);
-
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
+    const int cls = max_order <= 4 ? 0 : max_order <= 8 ? 1 : max_order <= 12 ? 2 : 3;
+    if (cls != CLASS) return;
+    const bool vec_own = (reinterpret_cast<uintptr_t>(sub) & 15) == 0;
+    const bool all_vec = __all_sync(0xffffffffu, !active || vec_own);
+    SeqRow* pr = s_rows[warp];
+    {
+        SeqRow row;
+        row.out = (g_seq_debug & 2) ? nullptr : sub;
+        row.bs = bs;
+        row.meta = (vec_own ? 1u : 0u) | (wasted << 8) | ((c == 0 ? ca : 0u) << 16);
+        pr[lane] = row;
+    }
+    __syncwarp();
+
     const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
     const bool any_wasted = __any_sync(0xffffffffu, active && wasted != 0);
     int32_t smin = 0, smax = 0;
 #define CLX_ROWS(T, UU, A) predict_seq_rows<T, UU, A, NARROW>(column, bs, order, shift, sp, active, tile, pr, s_pf[warp], lane, all_vec, any_wasted, smin, smax)
-    if (all_narrow) {
-        if (max_order <= 4) CLX_ROWS(4, 8, int);
-        else if (max_order <= 8) CLX_ROWS(8, 8, int);
-        else if (max_order <= 12) CLX_ROWS(12, 4, int);
-        else CLX_ROWS(32, 4, int);
-    } else {
-        if (max_order <= 4) CLX_ROWS(4, 8, long long);
-        else if (max_order <= 8) CLX_ROWS(8, 8, long long);
-        else if (max_order <= 12) CLX_ROWS(12, 4, long long);
-        else CLX_ROWS(32, 4, long long);
-    }
+    constexpr int T = CLASS == 0 ? 4 : CLASS == 1 ? 8 : CLASS == 2 ? 12 : 32;
+    constexpr int UU = CLASS <= 1 ? 8 : 4;
+    if (all_narrow) CLX_ROWS(T, UU, int);
+    else CLX_ROWS(T, UU, long long);
 #undef CLX_ROWS
     // The shortcuts taken above are exact only under conditions on the samples actually produced:
     //  * i32 accumulator: sum|coef| * max|sample| < 2^31;
@@ -488,6 +519,8 @@ size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames) {
 cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
                        const CoopPlan& plan, cudaStream_t stream, int which) {
+    static const int env_which = getenv("CLX_SEQ_WHICH") ? atoi(getenv("CLX_SEQ_WHICH")) : 3;  // measurements only
+    which &= env_which;
     const uint32_t CH = plan.channels;
     uint32_t ch_log2 = 0;
     while ((1u << ch_log2) < CH) ch_log2++;
@@ -503,18 +536,22 @@ cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fra
         if (which & 1)
             entropy_seq_kernel<true><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
                                                             rows, d_need_generic);
-        if (which & 2)
-            predict_seq_kernel<true><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2,
-                                                            rows, n_pwarps, d_need_generic);
+        if (which & 2) {
+#define CLX_PRE(N, C) predict_seq_kernel<N, C><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2, rows, n_pwarps, d_need_generic)
+            CLX_PRE(true, 0); CLX_PRE(true, 1); CLX_PRE(true, 2); CLX_PRE(true, 3);
+        }
     } else {
         if (which & 1)
             entropy_seq_kernel<false><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
                                                              rows, d_need_generic);
-        if (which & 2)
-            predict_seq_kernel<false><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2,
-                                                             rows, n_pwarps, d_need_generic);
+        if (which & 2) {
+            CLX_PRE(false, 0); CLX_PRE(false, 1); CLX_PRE(false, 2); CLX_PRE(false, 3);
+#undef CLX_PRE
+        }
     }
     return cudaGetLastError();
 }
 
 }  // namespace clx
+
+extern "C" void clx_debug_seq_flags(int flags) { cudaMemcpyToSymbol(clx::g_seq_debug, &flags, sizeof flags); }

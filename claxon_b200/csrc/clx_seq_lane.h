@@ -88,6 +88,13 @@ CLX_HD uint32_t hd_fsl(uint32_t hi, uint32_t lo, uint32_t n) {
     return n ? (hi << n) | (lo >> (32 - n)) : hi;
 #endif
 }
+CLX_HD uint32_t hd_bswap(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
 CLX_HD int32_t hd_sext(uint32_t v, uint32_t bits) {  // bits in [1, 32]
     return ((int32_t)(v << (32 - bits))) >> (32 - bits);
 }
@@ -98,7 +105,7 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 //   uint32_t word(uint32_t wi)            big-endian word `wi` of the frame (relative to its 16-byte aligned base)
 //   void ensure(uint32_t bitpos)          the next 2048 bits from bitpos are readable through word()
 //   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: take the slow path
-//   void seek_next(uint32_t wi), uint32_t next_word()   sequential word reads (the register window's refill)
+//   void seek_next(uint32_t wi), uint32_t next_raw()   sequential word reads, bytes as stored (the register window's refill)
 //   void select_channel(uint32_t ch)      subsequent stores go to channel ch's rows
 //   void store8(uint32_t t, const int32_t (&e)[8])   residuals t..t+7, t % 8 == 0
 //   void store1(uint32_t t, int32_t e)
@@ -108,7 +115,10 @@ struct SeqLane {
     SeqParams* params;  // the frame's CH records
     uint32_t bs, nch, ca, fbps, bit0, limit, byte_len;
     uint32_t o;           // bit cursor, relative to the frame's 16-byte aligned base
-    uint32_t W0, W1, W2;  // big-endian words o>>5, +1, +2 (maintained while mode == SEQ_RUN)
+    // Register window (maintained while mode == SEQ_RUN): big-endian words o>>5 and (o>>5)+1, and word
+    // (o>>5)+2 as loaded (little-endian): it is byte-swapped only when it moves up, one word later, so the
+    // swap never waits for the shared-memory load that produced it.
+    uint32_t W0, W1, W2;
     uint32_t mode, ch, t, n_left, parts_left, per, order, pbits;
     uint32_t k, K, Kneg, K30, c32k, thr;
     uint32_t consumed;
@@ -136,8 +146,9 @@ struct SeqLane {
     CLX_HD uint32_t bits(uint32_t pos, uint32_t n) { return n ? peek32(pos) >> (32 - n) : 0u; }  // n <= 32
     CLX_HD void window_seek() {
         const uint32_t wi = o >> 5;
-        W0 = io.word(wi); W1 = io.word(wi + 1); W2 = io.word(wi + 2);
-        io.seek_next(wi + 3);
+        W0 = io.word(wi); W1 = io.word(wi + 1);
+        io.seek_next(wi + 2);
+        W2 = io.next_raw();
     }
     CLX_HD void emit1(int32_t e) {  // one residual through the slow path
         if (NARROW && (e < -32768 || e > 32767)) { fail(); return; }
@@ -173,7 +184,7 @@ struct SeqLane {
             const uint32_t u = m * Kneg + (v + K30);  // (q << k) | r = (30 - m) * K + v
             e[i] = (int32_t)((u >> 1) ^ hd_neg_lsb(u));  // rice_to_signed, src/subframe.rs:157-170
             const uint32_t on = o + c32k - m;     // o + q + 1 + k
-            if ((on ^ o) >> 5) { W0 = W1; W1 = W2; W2 = io.next_word(); }
+            if ((on ^ o) >> 5) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
             o = on;
         }
         if (bad) {

@@ -80,7 +80,8 @@ typedef struct clx_options {
 } clx_options;
 #define CLX_OPT_NO_VERIFY_CRC 1u /* mimic claxon's cfg(fuzzing): skip CRC-8/CRC-16 checks */
 #define CLX_OPT_GENERIC_KERNEL_ONLY 2u /* testing: bypass the fast path */
-#define CLX_OPT_WARP_PER_FRAME 4u      /* testing: the warp-per-frame fast path instead of the lane-per-frame one */
+#define CLX_OPT_WARP_PER_FRAME 4u      /* the warp-per-frame fast path everywhere (default: only for small synchronous calls) */
+#define CLX_OPT_LANE_PER_FRAME 8u      /* the lane-per-frame fast path everywhere, also for small synchronous calls */
 
 typedef struct clx_ctx clx_ctx;     /* one per host thread / GPU; owns device scratch */
 typedef struct clx_batch clx_batch; /* a device-resident batch (bytes + descriptors + output) */

@@ -25,6 +25,7 @@ def ctx(request):
     """Every device path: the fast path (lane-per-frame entropy + lane-per-subframe prediction, with its
     fallback), the earlier warp-per-frame fast path, and the generic kernel alone."""
     import claxon_b200 as cb
-    c = cb.Context(device=0, generic_only=(request.param == "generic"), warp_per_frame=(request.param == "warp"))
+    c = cb.Context(device=0, generic_only=(request.param == "generic"), warp_per_frame=(request.param == "warp"),
+                   lane_per_frame=(request.param == "seq"))
     yield c
     c.close()

@@ -6,7 +6,7 @@ import claxon_b200 as cb
 from claxon_b200 import synth
 from oracle import oracle as O
 
-ctx = cb.Context(generic_only=('--generic' in sys.argv), warp_per_frame=('--warp' in sys.argv))
+ctx = cb.Context(generic_only=('--generic' in sys.argv), warp_per_frame=('--warp' in sys.argv), lane_per_frame=('--warp' not in sys.argv))
 
 def run(label, cfg):
     b = synth.generate(cfg)

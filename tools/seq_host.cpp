@@ -29,7 +29,7 @@ struct HostIO {
     }
     uint32_t wnext = 0;
     void seek_next(uint32_t wi) { wnext = wi; }
-    uint32_t next_word() { return word(wnext++); }
+    uint32_t next_raw() { return __builtin_bswap32(word(wnext++)); }
     void ensure(uint32_t) {}
     bool prefetch_group(uint32_t) { return true; }
     void select_channel(uint32_t ch) { column = frame_rows + ch * channel_stride; }
