@@ -57,7 +57,9 @@ struct DeviceIO {
         const bool in = q < qlim;
         const uint4* src = gbase + (in ? q : 0u);
         const uint32_t sz = in ? 16u : 0u;  // src-size 0: the destination is zero-filled
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+        // .cg: straight from L2.  32 lanes ask for 32 different lines; letting them allocate in L1 (.ca) costs the
+        // load/store unit far more than the second half of each 32-byte sector being fetched again later.
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
     }
     __device__ __forceinline__ uint32_t word(uint32_t wi) const {
         uint32_t v;
@@ -106,11 +108,11 @@ struct DeviceIOT : DeviceIO {
             v.y = __byte_perm((uint32_t)e[2], (uint32_t)e[3], 0x5410);
             v.z = __byte_perm((uint32_t)e[4], (uint32_t)e[5], 0x5410);
             v.w = __byte_perm((uint32_t)e[6], (uint32_t)e[7], 0x5410);
-            *reinterpret_cast<uint4*>(column + (uint64_t)t * (SEQ_ROW_BYTES / 8)) = v;
+            __stcs(reinterpret_cast<uint4*>(column + (uint64_t)t * (SEQ_ROW_BYTES / 8)), v);  // streaming: read once, much later
         } else {
             char* p = column + (uint64_t)t * (SEQ_ROW_BYTES / 4);
-            *reinterpret_cast<int4*>(p) = make_int4(e[0], e[1], e[2], e[3]);
-            *reinterpret_cast<int4*>(p + SEQ_ROW_BYTES) = make_int4(e[4], e[5], e[6], e[7]);
+            __stcs(reinterpret_cast<int4*>(p), make_int4(e[0], e[1], e[2], e[3]));
+            __stcs(reinterpret_cast<int4*>(p + SEQ_ROW_BYTES), make_int4(e[4], e[5], e[6], e[7]));
         }
     }
     __device__ __forceinline__ void store1(uint32_t t, int32_t e) {
