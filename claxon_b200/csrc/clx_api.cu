@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -18,6 +21,72 @@
 
 #include "claxon_b200.h"
 #include "clx_internal.h"
+
+// A few long-lived host threads for the per-call CRC-16 pass: spawning std::threads per call costs more
+// than the checksums themselves (6 MB per C2 batch).
+class HostPool {
+public:
+    explicit HostPool(unsigned n) {
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    unsigned size() const { return (unsigned)workers_.size(); }
+    // Runs fn(part, parts) for part = 0 .. parts-1: part 0 on the caller, the rest on the workers.
+    void run(unsigned parts, const std::function<void(unsigned, unsigned)>& fn) {
+        parts = std::max(1u, std::min(parts, size() + 1));
+        if (parts > 1) {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            parts_ = parts;
+            pending_ = parts - 1;
+            gen_++;
+        }
+        if (parts > 1) cv_.notify_all();
+        fn(0, parts);
+        if (parts > 1) {
+            std::unique_lock<std::mutex> l(m_);
+            done_.wait(l, [this] { return pending_ == 0; });
+            fn_ = nullptr;
+        }
+    }
+
+private:
+    void loop(unsigned idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(unsigned, unsigned)>* fn;
+            unsigned parts;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+                parts = parts_;
+            }
+            if (fn && idx + 1 < parts) {
+                (*fn)(idx + 1, parts);
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned, unsigned)>* fn_ = nullptr;
+    unsigned parts_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
 
 struct clx_ctx {
     int device = 0;
@@ -46,6 +115,7 @@ struct clx_ctx {
     clx_frame_result* h_results = nullptr; size_t h_results_cap = 0;  // results (D2H)
     std::vector<uint8_t> crc_verdict;     // per frame: CRC-16 of the claimed span matched
     unsigned host_threads = 1;
+    HostPool* pool = nullptr;   // created on first use
 };
 
 struct clx_batch {
@@ -109,13 +179,12 @@ void precompute_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* de
     ctx->crc_verdict.assign(n, 0);
     if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
     uint8_t* verdict = ctx->crc_verdict.data();
-    unsigned nt = std::min<unsigned>(ctx->host_threads, (unsigned)std::max<size_t>(1, n / 64));
+    unsigned nt = std::min<unsigned>(ctx->host_threads, (unsigned)std::max<size_t>(1, n / 32));
     if (nt <= 1) return precompute_crc_range(bytes, descs, verdict, 0, n);
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++)
-        th.emplace_back(precompute_crc_range, bytes, descs, verdict, n * t / nt, n * (t + 1) / nt);
-    precompute_crc_range(bytes, descs, verdict, 0, n / nt);
-    for (auto& x : th) x.join();
+    if (!ctx->pool) ctx->pool = new HostPool(ctx->host_threads - 1);
+    ctx->pool->run(nt, [&](unsigned part, unsigned parts) {
+        precompute_crc_range(bytes, descs, verdict, n * part / parts, n * (part + 1) / parts);
+    });
 }
 
 void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results, size_t n) {
@@ -193,7 +262,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
     if (opts && (opts->flags & CLX_OPT_GENERIC_KERNEL_ONLY)) ctx->use_coop = false;
     if (opts && (opts->flags & CLX_OPT_WARP_PER_FRAME)) ctx->warp_per_frame = true;
     if (opts && (opts->flags & CLX_OPT_LANE_PER_FRAME)) ctx->lane_per_frame_always = true;
-    ctx->host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    ctx->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     *out = ctx;
     return CLX_OK;
 }
@@ -208,6 +277,7 @@ void clx_ctx_destroy(clx_ctx* ctx) {
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    delete ctx->pool;
     delete ctx;
 }
 
