@@ -143,7 +143,7 @@ def cpu_decode_rate(batch, threads, min_seconds):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=8000)  # ~0.16 s of device time: long enough to average out host hiccups
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="claxon_b200", choices=["claxon_b200", "reference"])
     ap.add_argument("--workload", default="c2")
@@ -201,6 +201,9 @@ def main():
 
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout at some debug levels; this script's stdout is one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
