@@ -143,3 +143,92 @@ def test_lane_logic_on_corrupted_frames(harness):
             assert np.array_equal(out[o:o + n], ref[o:o + n])
             agreed += 1
         assert agreed > 0
+
+
+def run_frames(L, data, offs, lens, narrow):
+    """Decodes frames (bytes `data`, offsets/lengths) through the lane path; returns descs, out, res."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    descs, out_elems = cb.descs_from_offsets(data, np.asarray(offs, np.uint64), np.asarray(lens, np.uint32))
+    descs = np.ascontiguousarray(descs)
+    padded = np.concatenate([data, np.zeros(256, np.uint8)])
+    out = np.full(max(1, out_elems), 0x5A5A5A5A, np.int32)
+    res = np.zeros(len(offs), dtype=[("status", "<i4"), ("consumed", "<u4")])
+    L.seq_host_decode(padded.ctypes.data, data.size, descs.ctypes.data, len(offs), int(narrow), out.ctypes.data,
+                      res.ctypes.data, None)
+    return descs, out, res
+
+
+@pytest.mark.parametrize("name", ["pop", "short", "wasted_bits", "non_subset", "empty_vorbis_comment",
+                                  "repeated_vorbis_comment"])
+def test_lane_logic_on_reference_fixtures(harness, golden, name):
+    """The reference's own test streams (PCM pinned by the STREAMINFO MD5 / the order-20 KAT, see test_oracle_golden):
+    fixed-4 + Rice (pop), LPC-1 (short), wasted bits + 16-bit block-size code, high-order LPC + Rice2 + mid/side."""
+    data = golden[f"{name}__bytes"]
+    rows = golden[f"{name}__frames"]
+    exp = golden[f"{name}__pcm"]
+    frames = [r for r in rows if r[1] == 0 and r[3] > 0]
+    offs = [int(r[0]) for r in frames]
+    lens = [int(r[3]) for r in frames]
+    bps = int(frames[0][6])
+    for narrow in ([False, True] if bps <= 16 else [False]):
+        descs, out, res = run_frames(harness, data, offs, lens, narrow)
+        assert (res["status"] == 0).all(), (name, narrow, res)
+        assert np.array_equal(res["consumed"], np.asarray(lens, np.uint32))
+        pos = 0
+        for i, r in enumerate(frames):
+            n = int(r[4] * r[5])
+            o = int(descs[i]["out_offset"])
+            assert np.array_equal(out[o:o + n], exp[pos:pos + n]), (name, narrow, i)
+            pos += n
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lane_logic_random_configs_vs_oracle(harness, seed):
+    """Random shapes (every subframe type, orders 1..32, Rice and Rice2, wasted bits, long unary runs, 1..8 channels):
+    whatever the lane accepts must equal the oracle bit for bit; what the oracle accepts should rarely be declined."""
+    rng = np.random.default_rng(5000 + seed)
+    nch = int(rng.integers(1, 9))
+    bps = int(rng.choice([8, 12, 16, 20, 24]))
+    cfg = synth.SynthConfig(
+        seed=int(rng.integers(1, 2**31)), n_frames=int(rng.integers(1, 70)),
+        block_size=int(rng.choice([16, 192, 576, 1000, 1152, 2304, 4096, int(rng.integers(1, 5000))])),
+        n_channels=nch, bps=bps, stereo_mode=-1 if nch == 2 else 0,
+        type_mask=int(rng.integers(1, 16)), lpc_min_order=1, lpc_max_order=int(rng.integers(1, 33)),
+        qlp_precision=0, rice_mode=int(rng.choice([-1, -2])), rice_kmin=0, rice_kmax=14,
+        max_porder=int(rng.integers(0, 8)), rice2=int(rng.integers(0, 3)), wasted_max=int(rng.integers(0, 6)),
+        long_unary_per_mille=int(rng.choice([0, 50])))
+    b = synth.generate(cfg)
+    offs, lens = b.frame_offsets[:-1], b.frame_lengths
+    descs0, out_elems = cb.descs_from_offsets(b.data, offs, lens)
+    bad, st, ref = O.decode_batch(b.data, offs, lens, descs0["out_offset"], out_elems, n_threads=4)
+    assert bad == 0
+    for narrow in ([False, True] if bps <= 16 else [False]):
+        descs, out, res = run_frames(harness, b.data, offs, lens, narrow)
+        accepted = 0
+        for i in range(b.n_frames):
+            if res["status"][i] != 0:
+                continue
+            accepted += 1
+            o, n = int(descs[i]["out_offset"]), int(descs[i]["n_channels"]) * int(descs[i]["block_size"])
+            assert np.array_equal(out[o:o + n], ref[o:o + n]), (seed, narrow, i)
+            assert res["consumed"][i] == lens[i]
+        if not narrow:
+            assert accepted == b.n_frames, (seed, accepted, b.n_frames)  # the wide scratch holds any valid stream
+
+
+def test_lane_logic_wrapping_streams(harness):
+    """Streams whose samples wrap around i32 (reference: all arithmetic is wrapping, Appendix A.8): huge Rice2
+    residuals exercise the slow code path (codes longer than the 32-bit window) and the u32 wrap of (q << k) | r."""
+    cfg = synth.SynthConfig(n_frames=12, block_size=1024, n_channels=2, bps=16, stereo_mode=0, type_mask=8,
+                            lpc_min_order=1, lpc_max_order=8, qlp_precision=5, rice_mode=-2, rice_kmin=26,
+                            rice_kmax=29, rice2=1, residual_mean=2.0e8, max_porder=1)
+    b = synth.generate(cfg)
+    assert np.abs(b.pcm.astype(np.int64)).max() > 2**29
+    descs, out, res = run_frames(harness, b.data, b.frame_offsets[:-1], b.frame_lengths, False)
+    assert (res["status"] == 0).all()
+    for i in range(b.n_frames):
+        o = int(descs[i]["out_offset"]); lo, hi = int(b.pcm_offsets[i]), int(b.pcm_offsets[i + 1])
+        assert np.array_equal(out[o:o + hi - lo], b.pcm[lo:hi])
+    # the narrow scratch cannot hold these residuals: every frame must be declined, none decoded wrongly
+    descs, out, res = run_frames(harness, b.data, b.frame_offsets[:-1], b.frame_lengths, True)
+    assert (res["status"] != 0).all()
