@@ -182,7 +182,10 @@ struct SeqLane {
             const uint32_t m = hd_msb(hi);        // terminator at bit m: unary quotient q = 31 - m
             const uint32_t v = hi >> ((m - k) & 31u);  // K + r
             const uint32_t u = m * Kneg + (v + K30);  // (q << k) | r = (30 - m) * K + v
-            e[i] = (int32_t)((u >> 1) ^ hd_neg_lsb(u));  // rice_to_signed, src/subframe.rs:157-170
+            // rice_to_signed (src/subframe.rs:157-170): (u >> 1) ^ -(u & 1).  With u = 2h + b that is h for b = 0 and
+            // ~h = h - u for b = 1, i.e. h + (-b) * u in wrapping arithmetic: the multiply-add runs on the FMA pipe,
+            // which this loop leaves half idle, instead of a third ALU operation (the ALU pipe is what bounds it).
+            e[i] = (int32_t)((u >> 1) + hd_neg_lsb(u) * u);
             const uint32_t on = o + c32k - m;     // o + q + 1 + k
             if ((on ^ o) >> 5) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
             o = on;
