@@ -124,6 +124,27 @@ def load_traffic():
         return None
 
 
+def cpu_model():
+    """Model name of the host CPU (for the cpu_baseline record); never raises."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_single_thread_rate(batch, min_seconds=1.0):
+    """claxon is single-threaded: the same port on ONE host thread; None on any problem."""
+    try:
+        v, _, _ = cpu_decode_rate(batch, 1, min_seconds)
+        return v
+    except Exception:
+        return None
+
+
 def cpu_decode_rate(batch, threads, min_seconds):
     from oracle import oracle as O
     offs, lens, poffs = batch.frame_offsets[:-1], batch.frame_lengths, batch.pcm_offsets[:-1]
@@ -188,7 +209,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64",
             "data": "synthetic", "config": config, "bit_exact": bool(ok),
-            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                              "sample": f"{args.steps} x full {args.workload} batch ({batch.n_samples} samples)",
                              "note": "C restatement of claxon v0.4.3 (oracle/), frames sharded over threads; "
                                      "claxon itself is Rust and cannot be built here (no rustc)"},
@@ -314,9 +335,10 @@ def main():
     if rank == 0 and args.gpus == 1 and args.cpu_seconds > 0:
         cores = os.cpu_count() or 1
         v, reps, dt = cpu_decode_rate(hb, cores, args.cpu_seconds)
-        cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+        cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+               "one_thread": cpu_single_thread_rate(hb),
                "sample": f"{reps} x one full {args.workload} batch ({hb.n_samples} samples) in {dt:.1f}s, "
-                         f"frames sharded over {cores} threads"}
+                         f"frames sharded over {cores} threads (one_thread: the same port on a single thread, >= 1 s)"}
 
     if rank == 0:
         line = {
