@@ -384,9 +384,13 @@ class FrameReader:
     def read_batch(self, max_frames: int, buffer: np.ndarray | None = None) -> list[Block]:
         """Batched extension: demux + decode up to max_frames frames in one device pass."""
         L = self._ctx._L
+        nf, need = C.c_size_t(0), C.c_uint64(0)
+        st = L.clx_reader_plan_batch(self._h, max_frames, C.byref(nf), C.byref(need))  # demux ahead: exact buffer size
+        if st == EOF:
+            return []
+        _check(st, self._ctx)
         descs = np.zeros(max_frames, dtype=DESC_DTYPE)
-        remaining = self._buf.size - self.position()
-        cap = int(min(max_frames * 8 * 65535, remaining * 8 + 4096))  # >= any decodable amount
+        cap = max(1, int(need.value))
         if buffer is None or buffer.size < cap:
             buffer = np.empty(cap, dtype=np.int32)
         n = C.c_size_t(0)

@@ -82,6 +82,7 @@ SYMBOLS = {
     "clx_reader_streaminfo": (C.c_int, [_vp, C.POINTER(StreamInfoC)]),
     "clx_reader_next": (C.c_int, [_vp, _vp, _sz, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                   C.POINTER(C.c_uint64)]),
+    "clx_reader_plan_batch": (C.c_int, [_vp, _sz, C.POINTER(_sz), C.POINTER(C.c_uint64)]),
     "clx_reader_next_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, C.POINTER(_sz)]),
     "clx_reader_position": (C.c_uint64, [_vp]),
     "clx_reader_close": (None, [_vp]),

@@ -133,7 +133,12 @@ struct clx_batch {
     // one graph launch instead of five stream operations, which matters when a step is ~25 us.
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_launches = 0;   // kernel launches inside the graph
-    bool graph_failed = false;
+    cudaEvent_t ev_idle = nullptr; // without a graph: the previous decode of this batch has finished
+    // Frame CRC-16 (src/frame.rs:752-763): the batch's bytes never change, so the checksum of every claimed
+    // span is taken once, on the host, when the batch is created; clx_batch_read applies it.
+    std::vector<uint8_t> crc_ok;
+    std::vector<uint64_t> h_offset;
+    std::vector<uint32_t> h_len;
 };
 
 namespace {
@@ -202,6 +207,19 @@ void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, 
         }
         if (!ok) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
     }
+}
+
+void build_graph(clx_ctx* ctx, clx_batch* b);
+
+// Everything the kernels assume about a caller-supplied descriptor (the C ABI does not trust it).
+bool valid_desc(const clx_frame_desc& d, size_t nbytes, size_t out_elems) {
+    const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
+    const uint32_t bps = d.bits_per_sample;
+    return d.byte_offset <= nbytes && d.byte_len <= nbytes - d.byte_offset && d.header_len <= d.byte_len &&
+           d.n_channels >= 1 && d.n_channels <= 8 && d.block_size != 0 && d.byte_len <= (1u << 28) &&
+           !(d.channel_assignment >= 8 && d.n_channels != 2) && d.channel_assignment <= 10 &&
+           (bps == 0 || (bps >= 4 && bps <= 32)) &&  // 0: "not in the header" -> Unsupported, as the reference
+           d.out_offset <= out_elems && elems <= out_elems - d.out_offset;
 }
 
 // Chooses how a set of frames maps onto the cooperative kernel (frames per CTA, shared memory).
@@ -293,14 +311,9 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
     if (!ctx || (!bytes && nbytes) || (!descs && n_frames) || (!results && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
     if (n_frames == 0) return CLX_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    for (size_t i = 0; i < n_frames; i++) {
-        const clx_frame_desc& d = descs[i];
-        const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
-        if (d.byte_offset > nbytes || d.byte_len > nbytes - d.byte_offset || d.header_len > d.byte_len ||
-            d.n_channels < 1 || d.n_channels > 8 || d.block_size == 0 || d.byte_len > (1u << 28) ||
-            (d.channel_assignment >= 8 && d.n_channels != 2) || d.out_offset + elems > out_elems || (!out && elems))
-            return CLX_ERR_INVALID_ARGUMENT;
-    }
+    if (!out) return CLX_ERR_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n_frames; i++)
+        if (!valid_desc(descs[i], nbytes, out_elems)) return CLX_ERR_INVALID_ARGUMENT;
     const double t0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     // Chunks of frames are pipelined over the context's streams: H2D of chunk i+1 and D2H of
     // chunk i-1 overlap the kernels of chunk i.  A chunk covers a contiguous byte range and a
@@ -328,43 +341,62 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
             const clx_frame_desc& d = descs[i];
             s.b0 = std::min<uint64_t>(s.b0, d.byte_offset & ~15ull);
             s.b1 = std::max<uint64_t>(s.b1, d.byte_offset + d.byte_len);
-            s.o0 = std::min<uint64_t>(s.o0, d.out_offset & ~3ull);
+            s.o0 = std::min<uint64_t>(s.o0, d.out_offset);
             s.o1 = std::max<uint64_t>(s.o1, d.out_offset + (uint64_t)d.n_channels * d.block_size);
         }
+        // The device copy of the chunk's output keeps the host layout's alignment (offset mod 4 elements, so
+        // 16-byte stores stay possible) but the copy back covers exactly [o0, o1): it never touches an element
+        // before the chunk's first frame, so neighbouring chunks cannot overlap on the host side.
         for (size_t i = s.f0; i < s.f1; i++) {
             ctx->h_descs[i].byte_offset -= s.b0;
-            ctx->h_descs[i].out_offset -= s.o0;
+            ctx->h_descs[i].out_offset -= s.o0 & ~3ull;
         }
         spans.push_back(s);
     }
+    size_t enqueued = 0;  // chunks with work in flight
+    // On any failure after the first enqueue: nothing may still be writing into the caller's buffers on return.
+    auto drain = [&](int rc) {
+        for (size_t c = 0; c < enqueued && c < n_chunks; c++) cudaStreamSynchronize(ctx->streams[c]);
+        return rc;
+    };
+#define CUD(call)                                                         \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return drain(cuda_fail(ctx, e_, #call));   \
+    } while (0)
     for (size_t c = 0; c < n_chunks; c++) {
         const Span& s = spans[c];
         clx_ctx::Scratch& sc = ctx->scratch[c];
         cudaStream_t st = ctx->streams[c];
-        const size_t nb = (size_t)(s.b1 - s.b0), nf = s.f1 - s.f0, no = (size_t)(s.o1 - s.o0);
+        const size_t nb = (size_t)(s.b1 - s.b0), nf = s.f1 - s.f0, lead = (size_t)(s.o0 & 3), no = (size_t)(s.o1 - s.o0);
         int rc;
         const size_t nb_pad = ((nb + 63) & ~(size_t)63) + 128;  // whole 64-byte TMA chunks + look-ahead
-        if ((rc = grow(ctx, sc.d_bytes, sc.bytes_cap, nb_pad, 4096))) return rc;
-        if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return rc;
-        if ((rc = grow(ctx, sc.d_out, sc.out_cap, no + 4, 4096))) return rc;
-        if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return rc;
-        if (!sc.d_need_hi) CU(ctx, cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
-        CU(ctx, cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc),
-                                cudaMemcpyHostToDevice, st));
+        if ((rc = grow(ctx, sc.d_bytes, sc.bytes_cap, nb_pad, 4096))) return drain(rc);
+        if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return drain(rc);
+        if ((rc = grow(ctx, sc.d_out, sc.out_cap, lead + no + 4, 4096))) return drain(rc);
+        if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return drain(rc);
+        if (!sc.d_need_hi) CUD(cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
         const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf, n_frames <= kLatencyRegimeFrames);
-        if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return rc;
-        CU(ctx, clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results,
-                                   sc.d_need_hi, sc.d_params, plan, st, &ctx->launches));
-        CU(ctx, cudaMemcpyAsync(out + s.o0, sc.d_out, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(ctx->h_results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
+        if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return drain(rc);
+        enqueued = c + 1;
+        CUD(cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
+        CUD(cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc), cudaMemcpyHostToDevice, st));
+        CUD(clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results, sc.d_need_hi,
+                               sc.d_params, plan, st, &ctx->launches));
+        CUD(cudaMemcpyAsync(out + s.o0, sc.d_out + lead, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUD(cudaMemcpyAsync(ctx->h_results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
     }
+#ifdef CLX_EXPERIMENT
     static const bool trace = getenv("CLX_TRACE") != nullptr;
+#else
+    constexpr bool trace = false;
+#endif
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t1 = trace ? now() : 0;
     precompute_crc(ctx, bytes, descs, n_frames);  // host work, overlapped with the copies and kernels above
     const double t2 = trace ? now() : 0;
-    for (size_t c = 0; c < n_chunks; c++) CU(ctx, cudaStreamSynchronize(ctx->streams[c]));
+    for (size_t c = 0; c < n_chunks; c++) CUD(cudaStreamSynchronize(ctx->streams[c]));
+#undef CUD
     const double t3 = trace ? now() : 0;
     memcpy(results, ctx->h_results, n_frames * sizeof(clx_frame_result));
     apply_crc(ctx, bytes, descs, results, n_frames);
@@ -382,14 +414,8 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     if (!ctx || !out || (!bytes && nbytes) || (!descs && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
-    for (size_t i = 0; i < n_frames; i++) {
-        const clx_frame_desc& d = descs[i];
-        const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
-        if (d.byte_offset > nbytes || d.byte_len > nbytes - d.byte_offset || d.header_len > d.byte_len ||
-            d.n_channels < 1 || d.n_channels > 8 || d.block_size == 0 || d.byte_len > (1u << 28) ||
-            (d.channel_assignment >= 8 && d.n_channels != 2) || d.out_offset + elems > out_elems)
-            return CLX_ERR_INVALID_ARGUMENT;
-    }
+    for (size_t i = 0; i < n_frames; i++)
+        if (!valid_desc(descs[i], nbytes, out_elems)) return CLX_ERR_INVALID_ARGUMENT;
     clx_batch* b = new clx_batch();
     b->nbytes = nbytes;
     b->buf_bytes = ((nbytes + 63) & ~(size_t)63) + 128;  // whole 64-byte TMA chunks + look-ahead
@@ -411,42 +437,64 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
         clx_batch_destroy(ctx, b);
         return cuda_fail(ctx, e, "clx_batch_create");
     }
+    if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {
+        precompute_crc(ctx, bytes, descs, n_frames);
+        b->crc_ok = ctx->crc_verdict;
+    }
+    b->h_offset.resize(n_frames);
+    b->h_len.resize(n_frames);
+    for (size_t i = 0; i < n_frames; i++) { b->h_offset[i] = descs[i].byte_offset; b->h_len[i] = descs[i].byte_len; }
+    build_graph(ctx, b);
     *out = b;
     return CLX_OK;
 }
 
+}  // extern "C"
+
 namespace {
-// Enqueues one decode of a device-resident batch on `st`, through the batch's graph when possible.
-int enqueue_batch(clx_ctx* ctx, clx_batch* b, cudaStream_t st) {
-    static const bool no_graph = getenv("CLX_NO_GRAPH") != nullptr;
-    if (!no_graph && !b->graph && !b->graph_failed && b->n_frames > 0) {
-        cudaGraph_t g = nullptr;
-        uint64_t n = 0;
-        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
-        if (e == cudaSuccess) {
-            cudaError_t e1 = clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
-                                                b->d_need_hi, b->d_params, b->plan, st, &n);
-            e = cudaStreamEndCapture(st, &g);
-            if (e1 != cudaSuccess) e = e1;
-        }
-        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&b->graph, g, 0);
-        if (g) cudaGraphDestroy(g);
-        if (e != cudaSuccess || !b->graph) {
-            b->graph = nullptr;
-            b->graph_failed = true;
-            cudaGetLastError();
-        } else b->graph_launches = n;
+// Captures the batch's launch sequence once; called from clx_batch_create so that no decode ever pays for
+// (or is timed with) a graph instantiation.
+void build_graph(clx_ctx* ctx, clx_batch* b) {
+#ifdef CLX_EXPERIMENT
+    if (getenv("CLX_NO_GRAPH")) return;
+#endif
+    if (b->n_frames == 0) return;
+    cudaStream_t st = ctx->streams[0];
+    cudaGraph_t g = nullptr;
+    uint64_t n = 0;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        cudaError_t e1 = clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
+                                            b->d_need_hi, b->d_params, b->plan, st, &n);
+        e = cudaStreamEndCapture(st, &g);
+        if (e1 != cudaSuccess) e = e1;
     }
+    if (e == cudaSuccess && g) e = cudaGraphInstantiate(&b->graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess || !b->graph) {
+        b->graph = nullptr;
+        cudaGetLastError();
+    } else b->graph_launches = n;
+}
+
+// Enqueues one decode of a device-resident batch on `st`, through the batch's graph when there is one.
+int enqueue_batch(clx_ctx* ctx, clx_batch* b, cudaStream_t st) {
     if (b->graph) {
         CU(ctx, cudaGraphLaunch(b->graph, st));
         ctx->launches += b->graph_launches;
         return CLX_OK;
     }
+    // No graph: two decodes of one batch share its flag words and parameter records, so they must not overlap.
+    if (b->ev_idle) CU(ctx, cudaStreamWaitEvent(st, b->ev_idle, 0));
     CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
                                b->d_params, b->plan, st, &ctx->launches));
+    if (!b->ev_idle) CU(ctx, cudaEventCreateWithFlags(&b->ev_idle, cudaEventDisableTiming));
+    CU(ctx, cudaEventRecord(b->ev_idle, st));
     return CLX_OK;
 }
 }  // namespace
+
+extern "C" {
 
 int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index) {
     if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
@@ -477,7 +525,28 @@ int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, c
     int rc = clx_batch_sync(ctx, b);
     if (rc) return rc;
     if (out) CU(ctx, cudaMemcpy(out, b->d_out, std::min(out_elems, b->out_elems) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (results) CU(ctx, cudaMemcpy(results, b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+    if (results) {
+        CU(ctx, cudaMemcpy(results, b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+        if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {
+            std::vector<uint8_t> tmp;
+            for (size_t i = 0; i < b->n_frames; i++) {
+                if (results[i].status != CLX_OK) continue;
+                bool ok;
+                const uint32_t consumed = results[i].consumed;
+                if (consumed == b->h_len[i]) ok = b->crc_ok[i] != 0;
+                else {  // the frame ended before the end of the span it was given: checksum what it did consume
+                    if (consumed < 2 || consumed > b->h_len[i]) ok = false;
+                    else {
+                        tmp.resize(consumed);
+                        CU(ctx, cudaMemcpy(tmp.data(), b->d_bytes + b->h_offset[i], consumed, cudaMemcpyDeviceToHost));
+                        const uint16_t stored = (uint16_t)(((uint32_t)tmp[consumed - 2] << 8) | tmp[consumed - 1]);
+                        ok = clx_crc16(tmp.data(), consumed - 2) == stored;
+                    }
+                }
+                if (!ok) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
+            }
+        }
+    }
     return CLX_OK;
 }
 
@@ -487,6 +556,7 @@ void clx_batch_destroy(clx_ctx* ctx, clx_batch* b) {
     cudaFree(b->d_bytes); cudaFree(b->d_descs); cudaFree(b->d_out); cudaFree(b->d_results); cudaFree(b->d_need_hi);
     cudaFree(b->d_params);
     if (b->graph) cudaGraphExecDestroy(b->graph);
+    if (b->ev_idle) cudaEventDestroy(b->ev_idle);
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_stop) cudaEventDestroy(b->ev_stop);
     delete b;
@@ -500,32 +570,38 @@ int clx_ctx_run_steps(clx_ctx* ctx, clx_batch** batches, size_t n_batches, uint3
     if (!ctx || !batches || n_batches == 0 || !total_ms) return CLX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaSetDevice(ctx->device));
     n_streams = std::max<uint32_t>(1, std::min<uint32_t>(n_streams, (uint32_t)ctx->streams.size()));
-    cudaEvent_t start, stop;
-    std::vector<cudaEvent_t> done(n_streams);
-    CU(ctx, cudaEventCreate(&start));
-    CU(ctx, cudaEventCreate(&stop));
-    for (auto& e : done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaStream_t s0 = ctx->streams[0];
-    CU(ctx, cudaEventRecord(start, s0));
-    for (uint32_t s = 1; s < n_streams; s++) CU(ctx, cudaStreamWaitEvent(ctx->streams[s], start, 0));
-    for (uint32_t i = 0; i < steps; i++) {
-        clx_batch* b = batches[i % n_batches];
-        cudaStream_t st = ctx->streams[i % n_streams];
-        b->last_stream = st;
-        int rc = enqueue_batch(ctx, b, st);
-        if (rc) return rc;
-    }
-    for (uint32_t s = 1; s < n_streams; s++) {
-        CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));
-        CU(ctx, cudaStreamWaitEvent(s0, done[s], 0));
-    }
-    CU(ctx, cudaEventRecord(stop, s0));
-    CU(ctx, cudaEventSynchronize(stop));
-    CU(ctx, cudaEventElapsedTime(total_ms, start, stop));
-    cudaEventDestroy(start);
-    cudaEventDestroy(stop);
-    for (auto& e : done) cudaEventDestroy(e);
-    return CLX_OK;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    std::vector<cudaEvent_t> done(n_streams, nullptr);
+    auto body = [&]() -> int {
+        CU(ctx, cudaEventCreate(&start));
+        CU(ctx, cudaEventCreate(&stop));
+        for (auto& e : done) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaStream_t s0 = ctx->streams[0];
+        CU(ctx, cudaEventRecord(start, s0));
+        for (uint32_t s = 1; s < n_streams; s++) CU(ctx, cudaStreamWaitEvent(ctx->streams[s], start, 0));
+        for (uint32_t i = 0; i < steps; i++) {
+            clx_batch* b = batches[i % n_batches];
+            cudaStream_t st = ctx->streams[i % n_streams];
+            b->last_stream = st;
+            int rc = enqueue_batch(ctx, b, st);
+            if (rc) return rc;
+        }
+        for (uint32_t s = 1; s < n_streams; s++) {
+            CU(ctx, cudaEventRecord(done[s], ctx->streams[s]));
+            CU(ctx, cudaStreamWaitEvent(s0, done[s], 0));
+        }
+        CU(ctx, cudaEventRecord(stop, s0));
+        CU(ctx, cudaEventSynchronize(stop));
+        CU(ctx, cudaEventElapsedTime(total_ms, start, stop));
+        return CLX_OK;
+    };
+    const int rc = body();
+    if (rc != CLX_OK) cudaDeviceSynchronize();  // nothing of this call may still be running when it returns
+    if (start) cudaEventDestroy(start);
+    if (stop) cudaEventDestroy(stop);
+    for (auto& e : done)
+        if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 void* clx_batch_device_out(clx_batch* b) { return b ? b->d_out : nullptr; }
@@ -553,6 +629,10 @@ struct clx_reader {
     clx_streaminfo si{};
     std::vector<clx_frame_desc> descs;
     std::vector<clx_frame_result> results;
+    // frames demuxed ahead by clx_reader_plan_batch / clx_reader_next_batch, valid while pos == plan_pos
+    size_t plan_n = 0, plan_max = 0;
+    uint64_t plan_pos = ~0ull, plan_elems = 0;
+    int plan_stop = CLX_OK;
 };
 
 namespace {
@@ -608,6 +688,7 @@ void clx_reader_close(clx_reader* r) { delete r; }
 int clx_reader_next(clx_reader* r, int32_t* buffer, size_t capacity, uint32_t* block_size, uint32_t* channels,
                     uint64_t* time) {
     if (!r) return CLX_ERR_INVALID_ARGUMENT;
+    if (r->pos > r->n) return CLX_EOF;
     clx_frame_desc d;
     const size_t avail = r->n - r->pos;
     int st = clx_parse_frame_header(r->bytes + r->pos, avail, &d, r->ctx->flags);
@@ -635,33 +716,57 @@ int clx_reader_next(clx_reader* r, int32_t* buffer, size_t capacity, uint32_t* b
     return CLX_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Demuxes up to max_frames frames ahead of the reader's position (once per position).
+void plan(clx_reader* r, size_t max_frames) {
+    if (r->plan_pos == r->pos && r->plan_max == max_frames) return;
+    r->descs.resize(max_frames);
+    uint64_t next = r->pos, total = 0;
+    int stop = CLX_OK;
+    size_t n = 0;
+    if (r->pos > r->n) stop = CLX_EOF;
+    else n = clx_demux_frames(r->bytes, r->n, r->pos, r->descs.data(), max_frames, &next, &total, &stop, r->ctx->flags);
+    r->plan_n = n; r->plan_max = max_frames; r->plan_pos = r->pos; r->plan_elems = total; r->plan_stop = stop;
+}
+}  // namespace
+
+extern "C" {
+
+int clx_reader_plan_batch(clx_reader* r, size_t max_frames, size_t* n_frames, uint64_t* out_elems) {
+    if (!r || !n_frames || !out_elems) return CLX_ERR_INVALID_ARGUMENT;
+    *n_frames = 0;
+    *out_elems = 0;
+    if (max_frames == 0) return CLX_OK;
+    plan(r, max_frames);
+    if (r->plan_n == 0) return r->plan_stop;  // header-level error or CLX_EOF
+    *n_frames = r->plan_n;
+    *out_elems = r->plan_elems;
+    return CLX_OK;
+}
+
 int clx_reader_next_batch(clx_reader* r, size_t max_frames, int32_t* buffer, size_t capacity, clx_frame_desc* descs,
                           size_t* n_decoded) {
     if (!r || !n_decoded || !descs) return CLX_ERR_INVALID_ARGUMENT;
     *n_decoded = 0;
     if (max_frames == 0) return CLX_OK;
-    r->descs.resize(max_frames);
-    uint64_t next = r->pos, total = 0;
-    int stop = CLX_OK;
-    size_t n = clx_demux_frames(r->bytes, r->n, r->pos, r->descs.data(), max_frames, &next, &total, &stop,
-                                r->ctx->flags);
-    if (n == 0) return stop;  // header-level error or CLX_EOF
+    plan(r, max_frames);
+    size_t n = r->plan_n;
+    if (n == 0) return r->plan_stop;  // header-level error or CLX_EOF
     // fit the caller's buffer
     while (n > 0) {
         const clx_frame_desc& last = r->descs[n - 1];
         if (last.out_offset + (uint64_t)last.n_channels * last.block_size <= capacity) break;
         n--;
     }
-    if (n == 0) return CLX_ERR_INVALID_ARGUMENT;
+    if (n == 0 || !buffer) return CLX_ERR_INVALID_ARGUMENT;  // not even the first frame fits: see clx_reader_plan_batch
     r->results.resize(n);
     int st = clx_decode_frames(r->ctx, r->bytes, r->n, r->descs.data(), n, buffer, capacity, r->results.data());
     if (st) return st;
     size_t good = 0;
     while (good < n && r->results[good].status == CLX_OK) good++;
-    if (good == 0) {
-        // The very first frame failed.  If its window was a guess, retry through the exact path.
-        return r->results[0].status;
-    }
+    if (good == 0) return r->results[0].status;  // the very first frame failed
     for (size_t i = 0; i < good; i++) {
         descs[i] = r->descs[i];
         descs[i].byte_len = r->results[i].consumed;

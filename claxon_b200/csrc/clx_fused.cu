@@ -1,59 +1,50 @@
-// clx_seq.cu — the fast path of claxon_b200: sequential entropy decode (one lane per frame) +
-// prediction (one lane per subframe), two kernels joined by a warp-interleaved residual scratch.
+// clx_fused.cu — the throughput path of claxon_b200: an index pass (one lane per frame) and a fused
+// entropy-decode + prediction pass (one lane per subframe).  No residual ever touches memory.
 //
-//   1. `entropy_seq_kernel` — ONE LANE PER FRAME, 32 frames per warp.  The lane walks its frame's
-//      bitstream in claxon's own order (clx_seq_lane.h: subframe header, warm-up, LPC parameters,
-//      residual header, Rice partitions; reference src/subframe.rs:29-91, :236-380, :382-415,
-//      :651-701) with a three-word register window over a per-lane shared-memory ring that cp.async
-//      keeps 16 quads ahead.  Eight Rice codes per trip: funnel shift, clz, two shifts, one
-//      multiply-add, rice_to_signed — about 12 instructions per code, every lane busy.  Residuals go
-//      to the scratch as one 16-byte store per eight codes (i16 for streams of <= 16 bits, else
-//      two stores of i32), laid out so that a warp's stores form whole 512-byte rows.
-//   2. `predict_seq_kernel` — ONE LANE PER SUBFRAME.  predict_fixed / predict_lpc_* (src/subframe.rs:
-//      417-474, :524-614) are strictly serial recurrences (the floor in `>> qlp_shift` makes them
-//      non-associative), so the parallel axis is the set of subframes: coefficients and history
-//      register-resident, residual rows prefetched by cp.async six trips ahead (coalesced), eight
-//      samples per trip.  Samples leave through a swizzled 32x32 shared-memory transpose; the flush
-//      handles the two channels of a frame together, which turns the wasted-bits shift
-//      (src/subframe.rs:216-225) and the inter-channel decorrelation (src/frame.rs:319-389) into a
-//      few operations per PAIR of 16-byte vectors, and writes planar i32 as coalesced 16-byte stores.
+//   1. `index_frames_kernel` — ONE LANE PER FRAME, 32 frames per warp (clx_lanes.h: IndexLane).  FLAC
+//      carries no subframe lengths (reference src/frame.rs:702-742: channel n+1 starts where channel n
+//      ended), so one lane walks the frame once: subframe headers, warm-up samples and predictor
+//      parameters (src/subframe.rs:29-91, :382-415, :651-701) are parsed and recorded per subframe
+//      together with the bit at which its residual starts; the Rice codes of every channel but the last
+//      are only stepped over (src/subframe.rs:336-348: unary run + k bits), eight per trip.
+//   2. `decode_subframes_kernel` — ONE LANE PER SUBFRAME.  The lane starts at the recorded bit, decodes
+//      its Rice partitions eight codes per trip from a three-word register window over a per-lane
+//      shared-memory ring (src/subframe.rs:236-380) and feeds the residuals, still in registers, to the
+//      recurrence it runs itself: predict_fixed / predict_lpc_* (src/subframe.rs:417-474, :524-614) are
+//      strictly serial (the floor in `>> qlp_shift` makes them non-associative), so the parallel axis is
+//      the set of subframes — coefficients and history register-resident, eight samples per trip.
+//      Samples leave through a swizzled 32x32 shared-memory transpose; the flush handles the two channels
+//      of a frame together, which turns the wasted-bits shift (src/subframe.rs:216-225) and the
+//      inter-channel decorrelation (src/frame.rs:319-389) into a few operations per PAIR of 16-byte
+//      vectors, and writes planar i32 as whole 128-byte lines.
 //
+// HBM traffic per frame: its bytes once for the decode, the bytes of all channels but the last once more
+// for the index pass, 224 bytes of parameters per subframe, and the planar i32 output once.
 // Anything irregular is flagged (CLX_INTERNAL_NEED_GENERIC) and decoded by the generic kernel.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <cstdlib>
-
 #include "claxon_b200.h"
 #include "clx_internal.h"
-#include "clx_seq_lane.h"
+#include "clx_lanes.h"
 
 namespace clx {
 
 // ---------------------------------------------------------------------------------
-// Device IO policy of the entropy lane
+// Device IO policy of a lane: a ring of RQ 16-byte quads in shared memory, fed by cp.async
 // ---------------------------------------------------------------------------------
-// Measurement hook (tools/exp_*.py): bit 0 = the entropy kernel drops its scratch stores, bit 1 = the
-// prediction kernel drops its PCM stores.  Zero in the product; read once per kernel.
-__device__ int g_seq_debug = 0;
-
-constexpr uint32_t RQ = 16;           // ring: quads (16 bytes) per lane
-constexpr int ENT_SEQ_WARPS = 1;      // warps (of 32 frames) per CTA
-
+template <uint32_t RQ, uint32_t WAITN>
 struct DeviceIO {
-    uint32_t ring;        // shared-space byte address of the lane's ring (256 bytes, 256-byte aligned)
+    static constexpr uint32_t BYTES = RQ * 16;
+    uint32_t ring;        // shared-space byte address of the lane's ring (BYTES bytes, BYTES-aligned)
     uint32_t rot;         // 16 * (lane & 7): rotates the ring index so that lanes in step hit different banks
     const uint4* gbase;   // the frame's 16-byte aligned base
     uint32_t qlim;        // quads readable from gbase (beyond: zeros)
     uint32_t fq;          // next quad to request
     uint32_t wp;          // ring byte offset (unmasked) of the next word of the register window
-    char* rows0;          // channel 0's rows + lane * 16
-    char* column;         // current channel's column
-    uint64_t channel_stride;
-    bool drop_stores;     // measurement hook
 
     __device__ __forceinline__ void issue(uint32_t q) {
-        const uint32_t dst = ring | (((q << 4) + rot) & 0xF0u);
+        const uint32_t dst = ring | (((q << 4) + rot) & (BYTES - 16u));
         const bool in = q < qlim;
         const uint4* src = gbase + (in ? q : 0u);
         const uint32_t sz = in ? 16u : 0u;  // src-size 0: the destination is zero-filled
@@ -63,13 +54,13 @@ struct DeviceIO {
     }
     __device__ __forceinline__ uint32_t word(uint32_t wi) const {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (((wi << 2) + rot) & 0xFCu)) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (((wi << 2) + rot) & (BYTES - 4u))) : "memory");
         return __byte_perm(v, 0, 0x0123);
     }
     __device__ __forceinline__ void seek_next(uint32_t wi) { wp = (wi << 2) + rot; }
     __device__ __forceinline__ uint32_t next_raw() {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (wp & 0xFCu)) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (wp & (BYTES - 4u))) : "memory");
         wp += 4;
         return v;
     }
@@ -83,76 +74,64 @@ struct DeviceIO {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads, about
-    // 0.4 on average, so one (predicated) copy per group keeps the ring RQ quads ahead; a lane whose
-    // ring has fallen behind (a run of maximal codes) is sent to the slow path, whose ensure() refills
-    // it.  The group needs quads up to (bitpos >> 7) + 3: with fq >= (bitpos >> 7) + 10 they were
-    // requested at least 6 groups ago, so only copies older than that are waited for.
+    // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads (C2: 0.36
+    // on average), so one predicated copy per group keeps the ring ahead; a lane whose ring has fallen
+    // behind (a run of maximal codes) is sent to the slow path, whose ensure() refills it.  The group
+    // needs quads up to (bitpos >> 7) + 3; copies of the last WAITN groups may still be in flight.
     __device__ __forceinline__ bool prefetch_group(uint32_t bitpos) {
         const uint32_t q0 = bitpos >> 7;
         if (fq < q0 + RQ) { issue(fq); fq++; }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 6;" ::: "memory");
-        return fq >= q0 + 10;
+        asm volatile("cp.async.wait_group %0;" ::"n"(WAITN) : "memory");
+        return fq >= q0 + 4 + WAITN;
     }
-    __device__ __forceinline__ void select_channel(uint32_t ch) { column = rows0 + ch * channel_stride; }
-};
-
-template <bool NARROW>
-struct DeviceIOT : DeviceIO {
-    __device__ __forceinline__ void store8(uint32_t t, const int32_t (&e)[8]) {
-        if (drop_stores) return;
-        if (NARROW) {
-            uint4 v;
-            v.x = __byte_perm((uint32_t)e[0], (uint32_t)e[1], 0x5410);
-            v.y = __byte_perm((uint32_t)e[2], (uint32_t)e[3], 0x5410);
-            v.z = __byte_perm((uint32_t)e[4], (uint32_t)e[5], 0x5410);
-            v.w = __byte_perm((uint32_t)e[6], (uint32_t)e[7], 0x5410);
-            __stcs(reinterpret_cast<uint4*>(column + (uint64_t)t * (SEQ_ROW_BYTES / 8)), v);  // streaming: read once, much later
-        } else {
-            char* p = column + (uint64_t)t * (SEQ_ROW_BYTES / 4);
-            __stcs(reinterpret_cast<int4*>(p), make_int4(e[0], e[1], e[2], e[3]));
-            __stcs(reinterpret_cast<int4*>(p + SEQ_ROW_BYTES), make_int4(e[4], e[5], e[6], e[7]));
-        }
+    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t lane, const uint8_t* bytes, uint64_t buf_bytes,
+                                         uint64_t byte_offset) {
+        ring = ring_addr;
+        rot = (lane & 7u) << 4;
+        fq = 0;
+        wp = 0;
+        const uint64_t aligned = byte_offset & ~15ull;
+        gbase = reinterpret_cast<const uint4*>(bytes + aligned);
+        qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x1ffffffu);
     }
-    __device__ __forceinline__ void store1(uint32_t t, int32_t e) {
-        if (NARROW) *reinterpret_cast<int16_t*>(column + seq_elem_offset<true>(t)) = (int16_t)e;
-        else *reinterpret_cast<int32_t*>(column + seq_elem_offset<false>(t)) = e;
+    __device__ __forceinline__ void open_idle(uint32_t ring_addr, uint32_t lane, const uint8_t* bytes) {
+        ring = ring_addr;
+        rot = (lane & 7u) << 4;
+        fq = 0;
+        wp = 0;
+        gbase = reinterpret_cast<const uint4*>(bytes);
+        qlim = 0;
     }
 };
 
 // ---------------------------------------------------------------------------------
-// Kernel 1: entropy decode, one lane per frame
+// Kernel 1: index pass, one lane per frame
 // ---------------------------------------------------------------------------------
-template <bool NARROW>
-__global__ void __launch_bounds__(ENT_SEQ_WARPS * 32)
-entropy_seq_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
-                   uint32_t n_frames, clx_frame_result* __restrict__ results, SeqParams* __restrict__ params,
-                   char* __restrict__ scratch, uint32_t CH, uint32_t rows_per_channel, int* __restrict__ need_generic) {
-    __shared__ __align__(256) uint4 s_ring[ENT_SEQ_WARPS][32][RQ];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w = blockIdx.x * ENT_SEQ_WARPS + warp;
-    const uint32_t fidx = w * 32 + lane;
+constexpr uint32_t IDX_RQ = 16;
+using IndexIO = DeviceIO<IDX_RQ, 6>;
+
+__global__ void __launch_bounds__(32)
+index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
+                    uint32_t n_frames, clx_frame_result* __restrict__ results, SeqParams* __restrict__ params, uint32_t CH,
+                    int* __restrict__ need_generic) {
+    __shared__ __align__(256) uint4 s_ring[32][IDX_RQ];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t fidx = blockIdx.x * 32 + lane;
     const bool live = fidx < n_frames;
 
-    SeqLane<DeviceIOT<NARROW>, NARROW> L;
-    L.mode = SEQ_DONE; L.ok = true; L.slow_next = false; L.consumed = 0; L.n_left = 0; L.t = 0;
-    L.io.ring = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][lane][0]);
-    L.io.rot = (lane & 7u) << 4;
-    L.io.fq = 0;
-    L.io.wp = 0;
-    L.io.drop_stores = (g_seq_debug & 1) != 0;
-    L.io.channel_stride = (uint64_t)rows_per_channel * SEQ_ROW_BYTES;
-    L.io.rows0 = scratch + (uint64_t)w * CH * L.io.channel_stride + lane * 16;
-    L.io.column = L.io.rows0;
-    L.io.gbase = reinterpret_cast<const uint4*>(bytes);
-    L.io.qlim = 0;
+    IndexLane<IndexIO> L;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&s_ring[lane][0]);
     if (live) {
         const clx_frame_desc d = descs[fidx];
-        const uint64_t aligned = d.byte_offset & ~15ull;
-        L.io.gbase = reinterpret_cast<const uint4*>(bytes + aligned);
-        L.io.qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x1ffffffu);
+        L.rc.io.open(ring, lane, bytes, buf_bytes, d.byte_offset);
         L.init(d, params + (size_t)fidx * CH, CH);
+    } else {
+        clx_frame_desc d = {};
+        L.rc.io.open_idle(ring, lane, bytes);
+        L.init(d, params, CH);
+        L.mode = SEQ_DONE;
+        L.rc.ok = true;
     }
     while (__any_sync(0xffffffffu, !L.done())) {
         if (L.fast_ready()) L.fast_group();
@@ -161,19 +140,19 @@ entropy_seq_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const 
     }
     if (live) {
         clx_frame_result res;
-        res.status = L.ok ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
-        res.consumed = L.consumed;
+        res.status = L.ok() ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
+        res.consumed = 0;  // set by the lane that decodes the frame's last subframe
         results[fidx] = res;
-        if (!L.ok) *need_generic = 1;
+        if (!L.ok()) *need_generic = 1;
     }
 }
 
 // ---------------------------------------------------------------------------------
-// Kernel 2: prediction + wasted shift + decorrelation, one lane per subframe
+// Kernel 2: entropy decode + prediction + wasted shift + decorrelation, one lane per subframe
 // ---------------------------------------------------------------------------------
-constexpr int PRE_SEQ_WARPS = 2;
-constexpr int PF_SLOTS = 8;   // prefetch ring: units (8 samples per lane) it holds
-constexpr int PF_DEPTH = 6;   // units in flight
+constexpr int DEC_WARPS = 2;
+constexpr uint32_t DEC_RQ = 8;
+using SubIO = DeviceIO<DEC_RQ, 2>;
 
 // One trip of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
 // v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first, the terms
@@ -235,7 +214,7 @@ __device__ __forceinline__ int4 shl4(const int4& v, uint32_t s) {
 // the samples produced) that is mid + (side>>1) + (side&1) and mid - (side>>1), floor shifts.
 __device__ __forceinline__ void mid_side(int32_t& a, int32_t& b) {
     const int32_t h = b >> 1;
-    const int32_t l = a + h + (b & 1);
+    const int32_t l = a + b - h;  // side - (side >> 1) = (side >> 1) + (side & 1)
     b = a - h;
     a = l;
 }
@@ -281,11 +260,14 @@ __device__ __forceinline__ void seq_flush(const int32_t* tile, const SeqRow* row
     __syncwarp();
 }
 
-template <int TAPS, int U, typename ACC, bool NARROW>
-__device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column, uint32_t bs, uint32_t order, uint32_t shift,
-                                                 const SeqParams* __restrict__ sp, bool active, int32_t* tile,
-                                                 const SeqRow* pr, uint4* pf, uint32_t lane, bool all_vec, bool any_wasted,
-                                                 int32_t& smin, int32_t& smax) {
+// The body of a subframe lane: residuals from the lane's own Rice decoder, recurrence, tile, flush.
+// Every lane of the warp advances over the same sample index t (lanes whose block is shorter idle at the
+// end), so the 32x32 tile fills row by row in step and is flushed as whole lines.
+template <int TAPS, int U, typename ACC>
+__device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint32_t order, uint32_t shift,
+                                            const SeqParams* __restrict__ sp, bool active, int32_t* tile, const SeqRow* pr,
+                                            int32_t* slow_e, uint32_t lane, bool all_vec, bool any_wasted, int32_t& smin,
+                                            int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
     for (int j = 0; j < TAPS; j++) {
@@ -298,8 +280,15 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
     const uint32_t max_bs = __reduce_max_sync(0xffffffffu, active ? bs : 0u);
     const uint32_t min_bs = __reduce_min_sync(0xffffffffu, active ? bs : 0xffffffffu);
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
-    const uint32_t head_end = min(max_bs, (max_order + 31u) & ~31u);  // whole tiles
-    const uint32_t bulk_end = min_bs > head_end ? head_end + ((min_bs - head_end) & ~31u) : head_end;
+    const uint32_t head_end = min(max_bs, (max_order + 7u) & ~7u);  // whole groups of eight
+    const uint32_t bulk_end = min_bs > head_end ? head_end + ((min_bs - head_end) & ~7u) : head_end;
+
+    // Samples are staged in one of two 32x32 tiles; while a tile fills (four trips of 8 samples), the
+    // previous one is written out a quarter per trip, so that its shared-memory loads, the
+    // decorrelation and its global stores interleave with the decode of the next samples.
+    int32_t* fill = tile;
+    int32_t* drain = tile + 32 * 32;
+    bool have_drain = false;
 
     auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
         for (uint32_t t = t0; t < t1; t++) {
@@ -308,8 +297,7 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
             if (inside) {
                 if (t < order) val = sp->warm[t];
                 else {
-                    const int32_t r = NARROW ? (int32_t)*reinterpret_cast<const int16_t*>(column + seq_elem_offset<true>(t))
-                                             : *reinterpret_cast<const int32_t*>(column + seq_elem_offset<false>(t));
+                    const int32_t r = L.next();
                     long long acc = 0;
 #pragma unroll
                     for (int j = 0; j < TAPS; j++) acc += (long long)c[j] * (long long)h[j];
@@ -321,8 +309,8 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
 #pragma unroll
             for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
             h[0] = val;
-            tile[seq_tile_word(lane, t & 31)] = val;
-            if ((t & 31) == 31) seq_flush<true>(tile, pr, t - 31, lane, any_wasted);
+            fill[seq_tile_word(lane, t & 31)] = val;
+            if ((t & 31) == 31) seq_flush<true>(fill, pr, t - 31, lane, any_wasted);
         }
     };
     guarded(0, head_end);
@@ -330,49 +318,18 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
         int32_t v[TAPS + U];
 #pragma unroll
         for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
-        // Residual rows stream L2 -> shared memory by cp.async PF_DEPTH units ahead: lane l's 16 bytes of a
-        // row sit next to lane l+CH's, so a warp's copies are a few contiguous runs.  A unit = 8 samples.
-        constexpr int CPS = NARROW ? 1 : 2;  // 16-byte copies per unit
-        const uint32_t pf_s = (uint32_t)__cvta_generic_to_shared(pf) + lane * 16;
-        auto request = [&](uint32_t unit) {
-            const uint32_t t = min(head_end + unit * 8u, bulk_end - 8u);
-#pragma unroll
-            for (int q = 0; q < CPS; q++) {
-                const char* src = column + (uint64_t)(NARROW ? (t >> 3) : (t >> 2) + q) * SEQ_ROW_BYTES;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pf_s + ((unit % PF_SLOTS) * CPS + q) * 512u), "l"(src)
-                             : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-#pragma unroll
-        for (int p = 0; p < PF_DEPTH; p++) request(p);
-        auto fetch = [&](uint32_t unit, uint4& x, uint4& y) {  // the unit's residuals, shared memory -> registers
-            if (NARROW) x = pf[(unit % PF_SLOTS) * 32 + lane];
-            else { x = pf[((unit % PF_SLOTS) * 2) * 32 + lane]; y = pf[((unit % PF_SLOTS) * 2 + 1) * 32 + lane]; }
-        };
-        asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH - 1) : "memory");
-        uint4 x, y = make_uint4(0, 0, 0, 0), xn, yn = make_uint4(0, 0, 0, 0);
-        fetch(0, x, y);
-        // Samples are staged in one of two 32x32 tiles; while a tile fills (four trips of 8 samples), the
-        // previous one is written out a quarter per trip, so that its shared-memory loads, the
-        // decorrelation and its global stores interleave with the multiply-adds of the recurrence.
-        int32_t* fill = tile;
-        int32_t* drain = tile + 32 * 32;
-        bool have_drain = false;
-        uint32_t unit = 0;
-        for (uint32_t t = head_end; t < bulk_end; t += 8, unit++) {
-            request(unit + PF_DEPTH);
-            asm volatile("cp.async.wait_group %0;" ::"n"(PF_DEPTH - 1) : "memory");  // unit + 1 has landed
-            fetch(unit + 1, xn, yn);  // used by the next trip: its latency hides behind this one
+        for (uint32_t t = head_end; t < bulk_end; t += 8) {
             int32_t r[8];
-            if (NARROW) {
-                r[0] = (int32_t)(int16_t)(x.x & 0xffffu); r[1] = (int32_t)x.x >> 16;
-                r[2] = (int32_t)(int16_t)(x.y & 0xffffu); r[3] = (int32_t)x.y >> 16;
-                r[4] = (int32_t)(int16_t)(x.z & 0xffffu); r[5] = (int32_t)x.z >> 16;
-                r[6] = (int32_t)(int16_t)(x.w & 0xffffu); r[7] = (int32_t)x.w >> 16;
-            } else {
-                r[0] = (int32_t)x.x; r[1] = (int32_t)x.y; r[2] = (int32_t)x.z; r[3] = (int32_t)x.w;
-                r[4] = (int32_t)y.x; r[5] = (int32_t)y.y; r[6] = (int32_t)y.z; r[7] = (int32_t)y.w;
+            bool got = false;
+            if (active) {
+                L.prepare();
+                if (L.group_ready()) got = L.fast_group(r);
+            }
+            if (!got) {  // a partition boundary inside the group, a code longer than the window, verbatim ... or an idle lane
+                if (active)
+                    for (int i = 0; i < 8; i++) slow_e[i] = L.next();
+#pragma unroll
+                for (int i = 0; i < 8; i++) r[i] = active ? slow_e[i] : 0;
             }
 #pragma unroll
             for (int half = 0; half < 8 / U; half++) {
@@ -401,56 +358,56 @@ __device__ __forceinline__ void predict_seq_rows(const char* __restrict__ column
                 int32_t* tmp = fill; fill = drain; drain = tmp;
                 have_drain = true;
             }
-            x = xn; y = yn;
         }
-        if (have_drain) {  // the last tile
+        if (have_drain) {  // whatever of the last full tile has not been written yet (re-writing a quarter is harmless)
+            const uint32_t g0 = (bulk_end & ~31u) - 32;
 #pragma unroll
-            for (uint32_t i = 0; i < 4; i++) {
-                if (all_vec) seq_flush_quarter<false>(drain, pr, bulk_end - 32, i, lane, any_wasted);
-                else seq_flush_quarter<true>(drain, pr, bulk_end - 32, i, lane, any_wasted);
-            }
+            for (uint32_t i = 0; i < 4; i++) seq_flush_quarter<true>(drain, pr, g0, i, lane, any_wasted);
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the look-ahead copies past the bulk are never used
     }
     guarded(bulk_end, max_bs);
-    if (max_bs & 31) seq_flush<true>(tile, pr, max_bs & ~31u, lane, any_wasted);
+    if (max_bs & 31) seq_flush<true>(fill, pr, max_bs & ~31u, lane, any_wasted);
 }
 
 // One instance per order class (CLASS 0: max order of the warp <= 4, 1: <= 8, 2: <= 12, 3: <= 32), launched
-// back to back: a warp does its work in the instance of its class and leaves the others at once.  The
-// 8-tap instance then needs 80 registers instead of the 128 of the 32-tap one, i.e. half as many again
-// resident warps — which is what bounds this latency-chained kernel.
-template <bool NARROW, int CLASS>
-__global__ void __launch_bounds__(PRE_SEQ_WARPS * 32)
-predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, int32_t* __restrict__ out,
-                   clx_frame_result* __restrict__ results, const SeqParams* __restrict__ params,
-                   const char* __restrict__ scratch, uint32_t CH, uint32_t ch_log2, uint32_t rows_per_channel,
-                   uint32_t n_pwarps, int* __restrict__ need_generic) {
-    __shared__ __align__(16) int32_t s_tile[PRE_SEQ_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
-    __shared__ SeqRow s_rows[PRE_SEQ_WARPS][32];
-    __shared__ __align__(16) uint4 s_pf[PRE_SEQ_WARPS][PF_SLOTS * (NARROW ? 1 : 2) * 32];
+// back to back: a warp does its work in the instance of its class and leaves the others at once, so the
+// 8-tap instance is not charged the registers of the 32-tap one.
+template <int CLASS>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
+                        uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
+                        const SeqParams* __restrict__ params, uint32_t CH, uint32_t ch_log2, uint32_t n_pwarps,
+                        int* __restrict__ need_generic) {
+    __shared__ __align__(16) int32_t s_tile[DEC_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
+    __shared__ SeqRow s_rows[DEC_WARPS][32];
+    __shared__ __align__(128) uint4 s_ring[DEC_WARPS][32][DEC_RQ];
+    __shared__ int32_t s_slow[DEC_WARPS][32][8];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t pw = blockIdx.x * PRE_SEQ_WARPS + warp;  // CH prediction warps per entropy warp
+    const uint32_t pw = blockIdx.x * DEC_WARPS + warp;  // CH subframe warps per group of 32 frames
     if (pw >= n_pwarps) return;
     const uint32_t w = pw >> ch_log2, part = pw & (CH - 1);
-    const uint32_t j = part * (32u >> ch_log2) + (lane >> ch_log2);  // frame within the entropy warp
+    const uint32_t j = part * (32u >> ch_log2) + (lane >> ch_log2);  // frame within the group
     const uint32_t c = lane & (CH - 1);
     const uint32_t f = w * 32 + j;
     int32_t* tile = s_tile[warp];
-    const char* column = scratch + ((uint64_t)(w * CH + c) * rows_per_channel) * SEQ_ROW_BYTES + j * 16;
 
-    bool active = false, narrow_ok = true;
-    uint32_t bs = 0, order = 0, shift = 0, wasted = 0, ca = 0, absum = 0;
+    bool active = false, narrow_ok = true, last = false;
+    uint32_t bs = 0, order = 0, shift = 0, wasted = 0, ca = 0, absum = 0, bit0 = 0, byte_len = 0;
     const SeqParams* sp = params;
     int32_t* sub = nullptr;
+    SubLane<SubIO> L;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][lane][0]);
+    L.rc.io.open_idle(ring, lane, bytes);
+    L.init_idle();
     if (f < n_frames && results[f].status == CLX_OK) {
         const clx_frame_desc d = descs[f];
         if (c < d.n_channels) {
             sp = params + (size_t)f * CH + c;
             active = true;
+            last = c + 1 == d.n_channels;
             bs = d.block_size;
             order = (uint32_t)sp->order;
             shift = (uint32_t)sp->shift;
@@ -463,18 +420,24 @@ predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, 
             else if (d.channel_assignment == 8 || d.channel_assignment == 10) bits += (c == 1);
             // valid streams keep |sample| <= 2^(bits-1); anything beyond is caught by the check below
             narrow_ok = ((unsigned long long)absum << (bits - 1)) < (1ull << 31);
+            bit0 = (uint32_t)(d.byte_offset & 15) * 8;
+            byte_len = d.byte_len;
         }
     }
     if (!__any_sync(0xffffffffu, active)) return;
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
     const int cls = max_order <= 4 ? 0 : max_order <= 8 ? 1 : max_order <= 12 ? 2 : 3;
     if (cls != CLASS) return;
+    if (active) {
+        L.rc.io.open(ring, lane, bytes, buf_bytes, descs[f].byte_offset);
+        L.init(*sp, bs, bit0 + byte_len * 8);
+    }
     const bool vec_own = (reinterpret_cast<uintptr_t>(sub) & 15) == 0;
     const bool all_vec = __all_sync(0xffffffffu, !active || vec_own);
     SeqRow* pr = s_rows[warp];
     {
         SeqRow row;
-        row.out = (g_seq_debug & 2) ? nullptr : sub;
+        row.out = sub;
         row.bs = bs;
         row.meta = (vec_own ? 1u : 0u) | (wasted << 8) | ((c == 0 ? ca : 0u) << 16);
         pr[lane] = row;
@@ -484,20 +447,29 @@ predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, 
     const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
     const bool any_wasted = __any_sync(0xffffffffu, active && wasted != 0);
     int32_t smin = 0, smax = 0;
-#define CLX_ROWS(T, UU, A) predict_seq_rows<T, UU, A, NARROW>(column, bs, order, shift, sp, active, tile, pr, s_pf[warp], lane, all_vec, any_wasted, smin, smax)
+#define CLX_ROWS(T, UU, A) decode_rows<T, UU, A>(L, bs, order, shift, sp, active, tile, pr, s_slow[warp][lane], lane, all_vec, any_wasted, smin, smax)
     constexpr int T = CLASS == 0 ? 4 : CLASS == 1 ? 8 : CLASS == 2 ? 12 : 32;
     constexpr int UU = CLASS <= 1 ? 8 : 4;
     if (all_narrow) CLX_ROWS(T, UU, int);
     else CLX_ROWS(T, UU, long long);
 #undef CLX_ROWS
+    if (!active) return;
+    // The subframe must end inside the frame; the lane of the last subframe locates the CRC-16 footer
+    // (pad bits up to the byte boundary are skipped unchecked, src/frame.rs:744-754).
+    const uint32_t end_bit = L.finish();
+    bool redo = !L.ok();
+    if (last && !redo) {
+        const uint32_t consumed = ((end_bit - bit0 + 7) >> 3) + 2;
+        if (consumed > byte_len) redo = true;
+        else results[f].consumed = consumed;
+    }
     // The shortcuts taken above are exact only under conditions on the samples actually produced:
     //  * i32 accumulator: sum|coef| * max|sample| < 2^31;
     //  * mid/side without the wrapping intermediate: max|sample| << wasted < 2^29 on both channels.
     // A frame that fails either is re-decoded by the generic kernel (it never happens in a valid stream).
     const uint32_t m = max((uint32_t)smax, 0u - (uint32_t)smin);
-    bool redo = false;
-    if (active && all_narrow && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) redo = true;
-    if (active && ca == 10 && (((unsigned long long)m) << wasted) >= (1ull << 29)) redo = true;
+    if (all_narrow && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) redo = true;
+    if (ca == 10 && (((unsigned long long)m) << wasted) >= (1ull << 29)) redo = true;
     if (redo) {
         results[f].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
         *need_generic = 1;
@@ -507,53 +479,31 @@ predict_seq_kernel(const clx_frame_desc* __restrict__ descs, uint32_t n_frames, 
 // ---------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------
-static inline size_t seq_params_bytes(uint32_t n_warps, uint32_t CH) {
-    const size_t b = (size_t)n_warps * 32 * CH * sizeof(SeqParams);
-    return (b + 511) & ~(size_t)511;
-}
-
 size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames) {
     const uint32_t n_warps = (n_frames + 31) / 32;
-    const uint32_t rows = plan.narrow ? seq_rows_for<true>(plan.max_bs) : seq_rows_for<false>(plan.max_bs);
-    return seq_params_bytes(n_warps, plan.channels) + (size_t)n_warps * plan.channels * rows * SEQ_ROW_BYTES + 512;
+    const size_t b = (size_t)n_warps * 32 * plan.channels * sizeof(SeqParams);
+    return ((b + 511) & ~(size_t)511) + 512;
 }
 
 cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
                        const CoopPlan& plan, cudaStream_t stream, int which) {
-    static const int env_which = getenv("CLX_SEQ_WHICH") ? atoi(getenv("CLX_SEQ_WHICH")) : 3;  // measurements only
-    which &= env_which;
     const uint32_t CH = plan.channels;
     uint32_t ch_log2 = 0;
     while ((1u << ch_log2) < CH) ch_log2++;
     const uint32_t n_warps = (n_frames + 31) / 32;
-    const uint32_t rows = plan.narrow ? seq_rows_for<true>(plan.max_bs) : seq_rows_for<false>(plan.max_bs);
-    // 512-byte aligned: cudaMalloc'd base + 512-byte multiples
     SeqParams* params = reinterpret_cast<SeqParams*>(d_params);
-    char* scratch = reinterpret_cast<char*>(d_params) + seq_params_bytes(n_warps, CH);
-    dim3 g1((n_warps + ENT_SEQ_WARPS - 1) / ENT_SEQ_WARPS), b1(ENT_SEQ_WARPS * 32);
-    const uint32_t n_pwarps = n_warps * CH;
-    dim3 g2((n_pwarps + PRE_SEQ_WARPS - 1) / PRE_SEQ_WARPS), b2(PRE_SEQ_WARPS * 32);
-    if (plan.narrow) {
-        if (which & 1)
-            entropy_seq_kernel<true><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
-                                                            rows, d_need_generic);
-        if (which & 2) {
-#define CLX_PRE(N, C) predict_seq_kernel<N, C><<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, params, scratch, CH, ch_log2, rows, n_pwarps, d_need_generic)
-            CLX_PRE(true, 0); CLX_PRE(true, 1); CLX_PRE(true, 2); CLX_PRE(true, 3);
-        }
-    } else {
-        if (which & 1)
-            entropy_seq_kernel<false><<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, scratch, CH,
-                                                             rows, d_need_generic);
-        if (which & 2) {
-            CLX_PRE(false, 0); CLX_PRE(false, 1); CLX_PRE(false, 2); CLX_PRE(false, 3);
-#undef CLX_PRE
-        }
+    if (which & 1)
+        index_frames_kernel<<<n_warps, 32, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_results, params, CH,
+                                                        d_need_generic);
+    if (which & 2) {
+        const uint32_t n_pwarps = n_warps * CH;
+        dim3 g2((n_pwarps + DEC_WARPS - 1) / DEC_WARPS), b2(DEC_WARPS * 32);
+#define CLX_DEC(C) decode_subframes_kernel<C><<<g2, b2, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic)
+        CLX_DEC(0); CLX_DEC(1); CLX_DEC(2); CLX_DEC(3);
+#undef CLX_DEC
     }
     return cudaGetLastError();
 }
 
 }  // namespace clx
-
-extern "C" void clx_debug_seq_flags(int flags) { cudaMemcpyToSymbol(clx::g_seq_debug, &flags, sizeof flags); }

@@ -335,6 +335,7 @@ size_t clx_demux_frames(const uint8_t* bytes, size_t n, uint64_t start, clx_fram
     size_t count = 0;
     uint64_t pos = start, out_at = total_out_elems ? *total_out_elems : 0;
     int stop = CLX_OK;
+    if (start > n) { stop = CLX_EOF; max_frames = 0; }
     while (count < max_frames) {
         clx_frame_desc d;
         const int st = clx_parse_frame_header(bytes + pos, n - pos, &d, flags);

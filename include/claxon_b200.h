@@ -49,7 +49,9 @@ typedef struct clx_frame_desc {
     uint32_t sample_rate;        /* Hz, 0 = "from streaminfo"; not used by the decode */
     uint64_t number;             /* coded frame / sample number */
     uint64_t out_offset;         /* element (i32) offset of this frame's samples in the output;
-                                    multiple of 4 recommended (vectorised stores) */
+                                    multiple of 4 recommended (vectorised stores).  Elements of
+                                    `out` that lie between the first and the last frame of a call but
+                                    belong to no frame (alignment gaps) are unspecified afterwards. */
 } clx_frame_desc;
 
 #define CLX_FRAME_VARIABLE_BLOCKING 1u /* `number` is a sample number, else a frame number */
@@ -179,8 +181,15 @@ int clx_reader_streaminfo(const clx_reader* r, clx_streaminfo* si);
  * CLX_EOF == Ok(None). */
 int clx_reader_next(clx_reader* r, int32_t* buffer, size_t capacity, uint32_t* block_size,
                     uint32_t* channels, uint64_t* time);
+/* Batched extension, step 1 (optional): demuxes up to max_frames frames ahead of the reader's
+ * position WITHOUT decoding and reports how many were found and how many output elements
+ * clx_reader_next_batch(max_frames) needs for all of them (each frame aligned to 4 elements).
+ * The demux is cached: the following next_batch with the same max_frames does not repeat it.
+ * CLX_EOF at a clean end of stream; a header-level error if the very first frame has one. */
+int clx_reader_plan_batch(clx_reader* r, size_t max_frames, size_t* n_frames, uint64_t* out_elems);
 /* Batched extension: demuxes up to max_frames frames ahead and decodes them in one
- * device launch.  Stops before the first frame that fails (that frame's status is
+ * device launch.  Frames that do not fit `capacity` are left for the next call; if not even the
+ * first one fits the call returns CLX_ERR_INVALID_ARGUMENT (size the buffer with plan_batch).  Stops before the first frame that fails (that frame's status is
  * returned by the next call).  Returns the number of frames decoded in *n_decoded. */
 int clx_reader_next_batch(clx_reader* r, size_t max_frames, int32_t* buffer, size_t capacity,
                           clx_frame_desc* descs, size_t* n_decoded);

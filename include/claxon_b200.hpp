@@ -108,11 +108,15 @@ public:
     }
     // Batched extension: up to max_frames frames in one device pass.
     std::vector<Block> read_batch(size_t max_frames) {
+        size_t planned = 0;
+        uint64_t need = 0;
+        int st = clx_reader_plan_batch(r_, max_frames, &planned, &need);  // demux ahead: exact buffer size
+        if (st == CLX_EOF) return {};
+        if (st) throw Error(st);
         std::vector<clx_frame_desc> descs(max_frames);
-        const uint64_t remaining = n_ - clx_reader_position(r_);
-        std::vector<int32_t> pcm(size_t(remaining) * 8 + 4096);
+        std::vector<int32_t> pcm(size_t(need) + 4);
         size_t n = 0;
-        int st = clx_reader_next_batch(r_, max_frames, pcm.data(), pcm.size(), descs.data(), &n);
+        st = clx_reader_next_batch(r_, max_frames, pcm.data(), pcm.size(), descs.data(), &n);
         if (st == CLX_EOF) return {};
         if (st) throw Error(st);
         std::vector<Block> out;
