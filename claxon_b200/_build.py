@@ -49,7 +49,13 @@ def nvcc_path() -> str | None:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    """Compiles the CUDA extension for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compiles the CUDA extension for sm_100a with nvcc (cross-compiles without a GPU).
+
+    CLX_EXPERIMENT=1 builds and selects ``libclaxon_b200_exp.so`` instead: the same sources with the
+    measurement switches of tools/exp_*.py compiled in (-DCLX_EXPERIMENT); the product library has none."""
+    global LIB
+    if os.environ.get("CLX_EXPERIMENT"):
+        LIB = os.path.join(HERE, "libclaxon_b200_exp.so")
     if not force and not _newer(LIB, lib_deps()):
         return LIB
     nvcc = nvcc_path()

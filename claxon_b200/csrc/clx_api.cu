@@ -779,3 +779,17 @@ int clx_reader_next_batch(clx_reader* r, size_t max_frames, int32_t* buffer, siz
 }
 
 }  // extern "C"
+
+#ifdef CLX_EXPERIMENT
+// Measurement builds only (libclaxon_b200_exp.so, tools/exp_*.py): choose which passes of the throughput path a
+// batch's graph contains, and rebuild a batch's graph after changing the choice.
+extern "C" void clx_exp_set_which(int which) { clx::g_exp_which = which; }
+extern "C" void clx_exp_set_dyn_smem(int bytes) { clx::g_exp_dyn_smem = bytes; }
+extern "C" int clx_exp_rebuild_graph(clx_ctx* ctx, clx_batch* b) {
+    if (!ctx || !b) return CLX_ERR_INVALID_ARGUMENT;
+    cudaDeviceSynchronize();
+    if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+    build_graph(ctx, b);
+    return b->graph ? CLX_OK : CLX_ERR_CUDA;
+}
+#endif

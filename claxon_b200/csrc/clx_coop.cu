@@ -781,28 +781,12 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
     return cudaGetLastError();
 }
 
-#ifdef CLX_EXPERIMENT
-cudaError_t launch_entropy_only(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
-                                int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
-                                const CoopPlan& plan, cudaStream_t stream) {
-    dim3 g1((n_frames + ENT_WARPS - 1) / ENT_WARPS), b1(ENT_WARPS * 32);
-    entropy_frames_kernel<<<g1, b1, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
-                                                 reinterpret_cast<SubParams*>(d_params), plan.channels, d_need_generic);
-    return cudaGetLastError();
-}
-cudaError_t launch_predict_only(const clx_frame_desc* d_descs, uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results,
-                                int* d_need_generic, void* d_params, const CoopPlan& plan, cudaStream_t stream) {
-    const uint64_t slots = (uint64_t)n_frames * plan.channels;
-    dim3 g2((uint32_t)((slots + PRE_WARPS * 32 - 1) / (PRE_WARPS * 32))), b2(PRE_WARPS * 32);
-    predict_frames_kernel<<<g2, b2, 0, stream>>>(d_descs, n_frames, d_out, d_results, reinterpret_cast<SubParams*>(d_params),
-                                                 plan.channels, d_need_generic);
-    return cudaGetLastError();
-}
-#endif
 
 }  // namespace clx
 
+#ifdef CLX_COOP_STATS
 extern "C" void clx_debug_coop_stats(unsigned long long* out16, int reset) {
     cudaMemcpyFromSymbol(out16, clx::g_coop_stats, sizeof(unsigned long long) * 16);
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(clx::g_coop_stats, z, sizeof z); }
 }
+#endif

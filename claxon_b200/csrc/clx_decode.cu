@@ -697,20 +697,6 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
     int* d_need_hi = d_flags + 1;  // set by the 12-tap generic instance: some frames need 32 taps
     cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
-#ifdef CLX_EXPERIMENT  // measurement-only build: leave kernels out to see what bounds the steady state
-    static const int skip = getenv("CLX_DEBUG_SKIP") ? atoi(getenv("CLX_DEBUG_SKIP")) : 0;
-    if (skip) {
-        if (!(skip & 1)) launch_entropy_only(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, d_params, plan, stream);
-        if (!(skip & 2)) launch_predict_only(d_descs, n_frames, d_out, d_results, d_generic, d_params, plan, stream);
-        if (!(skip & 4)) {
-            decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
-                                                                 d_need_hi, d_generic, CLX_INTERNAL_NEED_GENERIC);
-            decode_frames_kernel<32><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
-                                                                 d_need_hi, d_need_hi, CLX_INTERNAL_NEED_HIGH_ORDER);
-        }
-        return cudaGetLastError();
-    }
-#endif
     if (plan.G > 0 && d_params != nullptr) {
         e = launch_coop(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, d_params, plan, stream);
         if (e != cudaSuccess) return e;

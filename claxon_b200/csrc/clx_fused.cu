@@ -152,7 +152,7 @@ index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const
 // ---------------------------------------------------------------------------------
 constexpr int DEC_WARPS = 2;
 constexpr uint32_t DEC_RQ = 8;
-using SubIO = DeviceIO<DEC_RQ, 2>;
+using SubIO = DeviceIO<DEC_RQ, 3>;
 
 // One trip of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
 // v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first, the terms
@@ -260,14 +260,50 @@ __device__ __forceinline__ void seq_flush(const int32_t* tile, const SeqRow* row
     __syncwarp();
 }
 
+// ---- shared-memory accesses by 32-bit shared-space address (no generic-pointer arithmetic in the hot loop) ----
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, int32_t a, int32_t b, int32_t c, int32_t d) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// The common case of seq_flush_quarter, straight-line: every lane of the warp active, every row 16-byte
+// aligned, no wasted bits, one stereo mode UCA (0 = none, 10 = mid/side) for every row pair, tile wholly
+// inside every row.
+//   tile_s: shared address of the tile to write out;  outp_s: shared address of the warp's 32 row pointers;
+//   lc0 / lc1: the lane's constant offsets into the tile for rows (2p, 2p+1) of its quarter (see decode_rows).
+template <int UCA>
+__device__ __forceinline__ void flush_quarter_fast(uint32_t tile_s, uint32_t outp_s, uint32_t g0, uint32_t quarter, uint32_t lane,
+                                                   uint32_t lc0, uint32_t lc1) {
+    const uint32_t a0 = tile_s + quarter * 1024u + lc0;
+    const int4 a = lds128(a0);
+    const int4 b = lds128(a0 + lc1);
+    unsigned long long p0, p1;  // rows 2 * (4 * quarter + (lane >> 3)) and the next
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "r"(outp_s + quarter * 64u + (lane >> 3) * 16u) : "memory");
+    int4 oa = a, ob = b;
+    if (UCA == 10) {  // src/frame.rs:371-389, see mid_side()
+        const int32_t hx = b.x >> 1, hy = b.y >> 1, hz = b.z >> 1, hw = b.w >> 1;
+        oa = make_int4(a.x + b.x - hx, a.y + b.y - hy, a.z + b.z - hz, a.w + b.w - hw);
+        ob = make_int4(a.x - hx, a.y - hy, a.z - hz, a.w - hw);
+    }
+    const uint32_t off = (g0 + (lane & 7u) * 4u) * 4u;  // bytes
+    *reinterpret_cast<int4*>(p0 + off) = oa;
+    *reinterpret_cast<int4*>(p1 + off) = ob;
+}
+
 // The body of a subframe lane: residuals from the lane's own Rice decoder, recurrence, tile, flush.
 // Every lane of the warp advances over the same sample index t (lanes whose block is shorter idle at the
 // end), so the 32x32 tile fills row by row in step and is flushed as whole lines.
-template <int TAPS, int U, typename ACC>
+//   tile_s: shared address of the warp's two tiles (8 KB, 8 KB-aligned: the other tile is `addr ^ 4096`).
+//   FMODE: 0 = general flush; 1 / 2 = flush_quarter_fast applies, without stereo decorrelation / mid-side.
+template <int TAPS, int U, typename ACC, int FMODE>
 __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint32_t order, uint32_t shift,
-                                            const SeqParams* __restrict__ sp, bool active, int32_t* tile, const SeqRow* pr,
-                                            int32_t* slow_e, uint32_t lane, bool all_vec, bool any_wasted, int32_t& smin,
-                                            int32_t& smax) {
+                                            const SeqParams* __restrict__ sp, bool active, int32_t* tile, uint32_t tile_s,
+                                            const SeqRow* pr, uint32_t outp_s, int32_t* slow_e, uint32_t lane, bool all_vec,
+                                            bool any_wasted, int32_t& smin, int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
     for (int j = 0; j < TAPS; j++) {
@@ -286,9 +322,9 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
     // Samples are staged in one of two 32x32 tiles; while a tile fills (four trips of 8 samples), the
     // previous one is written out a quarter per trip, so that its shared-memory loads, the
     // decorrelation and its global stores interleave with the decode of the next samples.
-    int32_t* fill = tile;
-    int32_t* drain = tile + 32 * 32;
+    uint32_t fill_s = tile_s;  // the tile being filled; the other one is fill_s ^ 4096
     bool have_drain = false;
+    auto tile_ptr = [&](uint32_t s_addr) { return tile + ((s_addr - tile_s) >> 2); };
 
     auto guarded = [&](uint32_t t0, uint32_t t1) {  // one sample at a time, every condition checked
         for (uint32_t t = t0; t < t1; t++) {
@@ -309,6 +345,7 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
 #pragma unroll
             for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
             h[0] = val;
+            int32_t* fill = tile_ptr(fill_s);
             fill[seq_tile_word(lane, t & 31)] = val;
             if ((t & 31) == 31) seq_flush<true>(fill, pr, t - 31, lane, any_wasted);
         }
@@ -318,19 +355,34 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
         int32_t v[TAPS + U];
 #pragma unroll
         for (int j = 0; j < TAPS; j++) v[j] = h[TAPS - 1 - j];
-        for (uint32_t t = head_end; t < bulk_end; t += 8) {
-            int32_t r[8];
+        const uint32_t l7 = lane & 7u, l3 = lane >> 3;
+        const uint32_t row_off = lane * 128u;  // the lane's row inside a tile
+        // flush_quarter_fast: rows r0 = 2 * (4 * quarter + l3) and r0 + 1; r0 & 7 = 2 * l3 whatever the quarter
+        const uint32_t lc0 = l3 * 256u + ((l7 ^ (2u * l3)) << 4);
+        const uint32_t lc1 = 128u + (((l7 ^ (2u * l3 + 1u)) << 4) - ((l7 ^ (2u * l3)) << 4));
+
+        // The loop is software-pipelined: a trip predicts the eight samples whose residuals the PREVIOUS trip
+        // decoded, and decodes — speculatively and branch-free, see RiceCursor::spec_group — the residuals of the
+        // next eight, in the same basic block: two independent dependency chains, one bound by the ALU pipe (bit
+        // scan), the other by the multiply-add pipe (recurrence), for the instruction scheduler to interleave.
+        int32_t rA[8], rB[8];
+        // residuals of the next eight samples by the ordinary route (the start, and whenever speculation fails)
+        auto produce = [&](int32_t (&dst)[8], bool try_fast) {
             bool got = false;
-            if (active) {
-                L.prepare();
-                if (L.group_ready()) got = L.fast_group(r);
+            if (try_fast) {
+                if (!L.fast()) L.prepare();  // partition switch, window seat
+                if (L.fast()) got = L.fast_group(dst);
             }
-            if (!got) {  // a partition boundary inside the group, a code longer than the window, verbatim ... or an idle lane
-                if (active)
-                    for (int i = 0; i < 8; i++) slow_e[i] = L.next();
+            if (!got) {  // a partition boundary inside the group, a code longer than the window, verbatim ...
+                for (int i = 0; i < 8; i++) slow_e[i] = L.next();
 #pragma unroll
-                for (int i = 0; i < 8; i++) r[i] = active ? slow_e[i] : 0;
+                for (int i = 0; i < 8; i++) dst[i] = slow_e[i];
             }
+        };
+        // prediction of samples t .. t+7 from their residuals, exactness bounds, staging in the tile
+        auto consume = [&](const int32_t (&r)[8], uint32_t t) {
+            // the lane's two 16-byte slots of this trip: columns (t & 31) .. +3 and +4 .. +7, swizzled by the row
+            const uint32_t slot0 = fill_s + row_off + (((((t >> 2) & 6u)) ^ l7) << 4);
 #pragma unroll
             for (int half = 0; half < 8 / U; half++) {
                 seq_trip<TAPS, U, ACC>(v, c, r + half * U, shift);
@@ -340,36 +392,60 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
                     smin = __vimin3_s32(smin, v[TAPS + i], v[TAPS + i + 1]);
                 }
 #pragma unroll
-                for (int q = 0; q < U / 4; q++) {
-                    const uint32_t col = (t + half * U + 4 * q) & 31;
-                    *reinterpret_cast<int4*>(fill + lane * 32 + (((col >> 2) ^ (lane & 7)) << 2)) =
-                        make_int4(v[TAPS + 4 * q], v[TAPS + 4 * q + 1], v[TAPS + 4 * q + 2], v[TAPS + 4 * q + 3]);
-                }
+                for (int q = 0; q < U / 4; q++)
+                    sts128(slot0 ^ ((uint32_t)(half * (U / 4) + q) << 4), v[TAPS + 4 * q], v[TAPS + 4 * q + 1], v[TAPS + 4 * q + 2],
+                           v[TAPS + 4 * q + 3]);
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) v[j] = v[j + U];
             }
+        };
+        // a quarter of the previous tile goes out; a full tile becomes the one to write out
+        auto after = [&](uint32_t t) {
             if (have_drain) {  // a tile inside [head_end, bulk_end) lies inside every active row
                 const uint32_t g0 = (t & ~31u) - 32, quarter = (t >> 3) & 3;
-                if (all_vec) seq_flush_quarter<false>(drain, pr, g0, quarter, lane, any_wasted);
-                else seq_flush_quarter<true>(drain, pr, g0, quarter, lane, any_wasted);
+                if (FMODE != 0) flush_quarter_fast<FMODE == 2 ? 10 : 0>(fill_s ^ 4096u, outp_s, g0, quarter, lane, lc0, lc1);
+                else if (all_vec) seq_flush_quarter<false>(tile_ptr(fill_s ^ 4096u), pr, g0, quarter, lane, any_wasted);
+                else seq_flush_quarter<true>(tile_ptr(fill_s ^ 4096u), pr, g0, quarter, lane, any_wasted);
             }
-            if (((t + 8) & 31) == 0) {  // the tile is full: it becomes the one to write out
+            if (((t + 8) & 31) == 0) {
                 __syncwarp();
-                int32_t* tmp = fill; fill = drain; drain = tmp;
+                fill_s ^= 4096u;
                 have_drain = true;
             }
+        };
+        auto step = [&](const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
+            // codes per window refill: what every lane on the fast path allows (by its partition's Rice parameter)
+            const uint32_t nc = __reduce_min_sync(0xffffffffu, L.spec_cap());
+            bool good;
+            if (nc == 2) { good = L.template spec_group<2>(prod); consume(cons, t); }
+            else { good = L.template spec_group<1>(prod); consume(cons, t); }
+            if (!good && active) produce(prod, true);  // rare
+            after(t);
+        };
+        if (active) produce(rA, true);
+        uint32_t t = head_end;
+        while (t + 16 < bulk_end) {
+            step(rA, rB, t);
+            step(rB, rA, t + 8);
+            t += 16;
         }
+        if (t + 8 < bulk_end) {
+            step(rA, rB, t);
+            t += 8;
+            consume(rB, t);
+        } else consume(rA, t);
+        after(t);
         if (have_drain) {  // whatever of the last full tile has not been written yet (re-writing a quarter is harmless)
             const uint32_t g0 = (bulk_end & ~31u) - 32;
 #pragma unroll
-            for (uint32_t i = 0; i < 4; i++) seq_flush_quarter<true>(drain, pr, g0, i, lane, any_wasted);
+            for (uint32_t i = 0; i < 4; i++) seq_flush_quarter<true>(tile_ptr(fill_s ^ 4096u), pr, g0, i, lane, any_wasted);
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < TAPS; j++) h[j] = v[TAPS - 1 - j];
     }
     guarded(bulk_end, max_bs);
-    if (max_bs & 31) seq_flush<true>(fill, pr, max_bs & ~31u, lane, any_wasted);
+    if (max_bs & 31) seq_flush<true>(tile_ptr(fill_s), pr, max_bs & ~31u, lane, any_wasted);
 }
 
 // One instance per order class (CLASS 0: max order of the warp <= 4, 1: <= 8, 2: <= 12, 3: <= 32), launched
@@ -381,8 +457,9 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
                         uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
                         const SeqParams* __restrict__ params, uint32_t CH, uint32_t ch_log2, uint32_t n_pwarps,
                         int* __restrict__ need_generic) {
-    __shared__ __align__(16) int32_t s_tile[DEC_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
+    __shared__ __align__(8192) int32_t s_tile[DEC_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
     __shared__ SeqRow s_rows[DEC_WARPS][32];
+    __shared__ __align__(16) int32_t* s_outp[DEC_WARPS][32];
     __shared__ __align__(128) uint4 s_ring[DEC_WARPS][32][DEC_RQ];
     __shared__ int32_t s_slow[DEC_WARPS][32][8];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -441,17 +518,33 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
         row.bs = bs;
         row.meta = (vec_own ? 1u : 0u) | (wasted << 8) | ((c == 0 ? ca : 0u) << 16);
         pr[lane] = row;
+        s_outp[warp][lane] = sub;
     }
     __syncwarp();
 
     const bool all_narrow = __all_sync(0xffffffffu, !active || narrow_ok);
     const bool any_wasted = __any_sync(0xffffffffu, active && wasted != 0);
+    // flush_quarter_fast: full warp, aligned rows, no wasted bits, and one stereo mode on every row pair
+    // (with one channel slot per frame, rows 2p and 2p+1 are unrelated frames: mode 0)
+    const uint32_t pair_ca = CH >= 2 ? __shfl_sync(0xffffffffu, ca, lane & ~1u) : 0u;
+    const uint32_t ca0 = __shfl_sync(0xffffffffu, pair_ca, 0);
+    const bool fast_flush = __all_sync(0xffffffffu, active && vec_own && wasted == 0 && pair_ca == ca0);
+    const int fmode = !fast_flush ? 0 : ca0 == 0 ? 1 : ca0 == 10 ? 2 : 0;
     int32_t smin = 0, smax = 0;
-#define CLX_ROWS(T, UU, A) decode_rows<T, UU, A>(L, bs, order, shift, sp, active, tile, pr, s_slow[warp][lane], lane, all_vec, any_wasted, smin, smax)
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t outp_s = (uint32_t)__cvta_generic_to_shared(&s_outp[warp][0]);
+#define CLX_ROWS(T, UU, A, F) decode_rows<T, UU, A, F>(L, bs, order, shift, sp, active, tile, tile_s, pr, outp_s, s_slow[warp][lane], lane, all_vec, any_wasted, smin, smax)
     constexpr int T = CLASS == 0 ? 4 : CLASS == 1 ? 8 : CLASS == 2 ? 12 : 32;
     constexpr int UU = CLASS <= 1 ? 8 : 4;
-    if (all_narrow) CLX_ROWS(T, UU, int);
-    else CLX_ROWS(T, UU, long long);
+    if (all_narrow) {
+        if (fmode == 2) CLX_ROWS(T, UU, int, 2);
+        else if (fmode == 1) CLX_ROWS(T, UU, int, 1);
+        else CLX_ROWS(T, UU, int, 0);
+    } else {
+        if (fmode == 2) CLX_ROWS(T, UU, long long, 2);
+        else if (fmode == 1) CLX_ROWS(T, UU, long long, 1);
+        else CLX_ROWS(T, UU, long long, 0);
+    }
 #undef CLX_ROWS
     if (!active) return;
     // The subframe must end inside the frame; the lane of the last subframe locates the CRC-16 footer
@@ -479,6 +572,11 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
 // ---------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------
+#ifdef CLX_EXPERIMENT
+int g_exp_which = 3;
+int g_exp_dyn_smem = 0;  // extra dynamic shared memory per decode CTA: lowers occupancy (measurement only)
+#endif
+
 size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames) {
     const uint32_t n_warps = (n_frames + 31) / 32;
     const size_t b = (size_t)n_warps * 32 * plan.channels * sizeof(SeqParams);
@@ -488,6 +586,9 @@ size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames) {
 cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
                        const CoopPlan& plan, cudaStream_t stream, int which) {
+#ifdef CLX_EXPERIMENT
+    which &= g_exp_which;
+#endif
     const uint32_t CH = plan.channels;
     uint32_t ch_log2 = 0;
     while ((1u << ch_log2) < CH) ch_log2++;
@@ -499,7 +600,12 @@ cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fra
     if (which & 2) {
         const uint32_t n_pwarps = n_warps * CH;
         dim3 g2((n_pwarps + DEC_WARPS - 1) / DEC_WARPS), b2(DEC_WARPS * 32);
-#define CLX_DEC(C) decode_subframes_kernel<C><<<g2, b2, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic)
+#ifdef CLX_EXPERIMENT
+        const size_t dyn = (size_t)g_exp_dyn_smem;
+#else
+        const size_t dyn = 0;
+#endif
+#define CLX_DEC(C) decode_subframes_kernel<C><<<g2, b2, dyn, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic)
         CLX_DEC(0); CLX_DEC(1); CLX_DEC(2); CLX_DEC(3);
 #undef CLX_DEC
     }

@@ -41,11 +41,8 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
                           void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
 #ifdef CLX_EXPERIMENT
-cudaError_t launch_entropy_only(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
-                                int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
-                                const CoopPlan& plan, cudaStream_t stream);
-cudaError_t launch_predict_only(const clx_frame_desc* d_descs, uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results,
-                                int* d_need_generic, void* d_params, const CoopPlan& plan, cudaStream_t stream);
+extern int g_exp_which;  // measurement builds only: bit 0 = index pass, bit 1 = decode pass
+extern int g_exp_dyn_smem;
 #endif
 
 }  // namespace clx

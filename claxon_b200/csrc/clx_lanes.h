@@ -108,28 +108,46 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 // ---------------------------------------------------------------------------------
 // Bit window + Rice partition state shared by both lanes
 // ---------------------------------------------------------------------------------
+// Codes of a partition are taken two per window refill when its Rice parameter is at most PAIR_KMAX, else one
+// (see codes8()).  A pair needs its two codes to be at most 32 bits long together; the bound is low because a
+// lane that fails takes its whole WARP through the slow branch: the per-lane failure rate has to be ~1e-4 per
+// group, i.e. (two-sided geometric residuals, mean quotient ~1) quotient sums above ~18 only.
+constexpr uint32_t PAIR_KMAX = 6;
+
 template <class IO>
 struct RiceCursor {
     IO io;
     uint32_t o;           // bit cursor, relative to the frame's 16-byte aligned base
     uint32_t limit;       // first bit past the frame's available bytes
-    // Register window (valid while !need_seek): big-endian words o>>5 and (o>>5)+1, and word (o>>5)+2 as
-    // loaded (little-endian): it is byte-swapped only when it moves up, one word later, so the swap never
+    // Register window over the words at o >> 5 (valid while n_fast != 0): W0, W1 big-endian, W2 the next word
+    // as loaded (little-endian).  W2 is byte-swapped only when it moves up, one refill later, so the swap never
     // waits for the shared-memory load that produced it.
     uint32_t W0, W1, W2;
     uint32_t n_left, parts_left, per, order, pbits;
-    uint32_t k, Kneg, K30, c32k, thr;
-    bool ok, need_seek, first_part;
+    uint32_t k, Kneg, K30, c32k;
+    uint32_t ncap;        // codes per window refill this partition allows: 2 or 1
+    uint32_t n_fast;      // groups of eight codes the fast path may take before anything else has to happen
+    bool ok, first_part;
 
-    CLX_HD void fail() { ok = false; n_left = 0; parts_left = 0; }
+    CLX_HD void reset(uint32_t start_bit, uint32_t limit_bit) {
+        o = start_bit; limit = limit_bit;
+        W0 = W1 = W2 = 0;
+        n_left = 0; parts_left = 0; per = 0; order = 0; pbits = 4;
+        k = 0; Kneg = 0xffffffffu; K30 = 30; c32k = 32; ncap = 1;
+        n_fast = 0;
+        ok = true; first_part = false;
+    }
+    CLX_HD void fail() { ok = false; n_left = 0; parts_left = 0; n_fast = 0; }
     CLX_HD uint32_t peek32(uint32_t pos) { return hd_fsl(io.word(pos >> 5), io.word((pos >> 5) + 1), pos); }
     CLX_HD uint32_t bits(uint32_t pos, uint32_t n) { return n ? peek32(pos) >> (32 - n) : 0u; }  // n <= 32
+    // Seats the register window at the cursor and opens the fast path for the rest of the partition.
     CLX_HD void window_seek() {
+        io.ensure(o);
         const uint32_t wi = o >> 5;
         W0 = io.word(wi); W1 = io.word(wi + 1);
         io.seek_next(wi + 2);
         W2 = io.next_raw();
-        need_seek = false;
+        n_fast = n_left >> 3;
     }
 
     // residual header (src/subframe.rs:236-304) at the cursor; `bs` = block size, `ord` = predictor order
@@ -148,13 +166,14 @@ struct RiceCursor {
         parts_left = n_part;
         first_part = true;
         n_left = 0;
-        need_seek = true;
+        n_fast = 0;
     }
     // partition header (src/subframe.rs:310-319, :358-367)
     CLX_HD void do_part() {
         io.ensure(o);
         k = bits(o, pbits);
         o += pbits;
+        n_fast = 0;
         if (k == (1u << pbits) - 1u) { fail(); return; }  // escape code: Unsupported in the reference
         n_left = first_part ? per - order : per;
         first_part = false;
@@ -163,12 +182,11 @@ struct RiceCursor {
         K30 = 30u * K;
         Kneg = 0u - K;
         c32k = 32u + k;
-        thr = 1u << k;  // a code fits the 32-bit window iff unary + terminator + k bits <= 32, i.e. hi >= 2^k
-        need_seek = true;
+        ncap = k <= PAIR_KMAX ? 2u : 1u;
         if (o > limit) fail();
     }
     // Moves to the partition that holds the next residual (empty partitions still carry a parameter,
-    // src/subframe.rs:283-288) and re-seats the register window.  False: nothing left or failed.
+    // src/subframe.rs:283-288).  False: nothing left, or failed.
     CLX_HD bool settle() {
         while (n_left == 0) {
             if (!ok || parts_left == 0) return false;
@@ -176,58 +194,98 @@ struct RiceCursor {
         }
         return ok;
     }
-    CLX_HD bool group_ready() const { return ok && !need_seek && n_left >= 8; }
-    CLX_HD void prepare() {  // before a group of eight codes
+    // Called when n_fast == 0 and a group of eight is wanted: partition switch and window seat.
+    CLX_HD void prepare() {
         if (!ok) return;
         if (n_left == 0 && parts_left != 0) settle();
-        if (ok && need_seek && n_left >= 8) { io.ensure(o); window_seek(); }
+        if (ok && n_left >= 8) window_seek();
     }
 
-    // ---- eight Rice codes (src/subframe.rs:336-348), all inside the 32-bit window: values ----
-    // Precondition group_ready().  The eight codes are decoded straight through; if any of them did not
-    // fit the window (hi < thr), what came after it is meaningless (but harmless: every shared-memory
-    // address is masked into the lane's ring), the cursor is put back and the caller takes the slow path.
-    CLX_HD bool fast_group(int32_t (&e)[8]) {
-        if (!io.prefetch_group(o)) { need_seek = true; return false; }
-        const uint32_t o0 = o;
+    // (q << k) | r of the code whose 32-bit window is `hi` with its terminator at bit m, then rice_to_signed
+    // (src/subframe.rs:157-170): (u >> 1) ^ -(u & 1).
+    CLX_HD int32_t code_value(uint32_t hi, uint32_t m) const {
+        const uint32_t v = hi >> ((m - k) & 31u);  // K + r
+        const uint32_t u = m * Kneg + (v + K30);   // (q << k) | r = (30 - m) * K + v,  q = 31 - m
+        return (int32_t)((u >> 1) ^ hd_neg_lsb(u));
+    }
+
+    // ---- eight Rice codes (src/subframe.rs:336-348) from the register window ----
+    // NC codes share one 32-bit window and one refill test: the window of the next code is the previous one's
+    // shifted left by its length (zeros come in at the bottom), which is all it needs as long as the NC codes
+    // TOGETHER are at most 32 bits long.  A code that does not fit — its terminator or its remainder beyond the
+    // window, or no terminator at all (bfind of 0 is 0xffffffff) — makes the sum of the lengths exceed 32, so
+    // that one comparison per refill covers everything; what was decoded after such a code is meaningless
+    // (but harmless: every shared-memory address is masked into the lane's ring) and `bad` is returned.
+    // NC = 1 takes any code of up to 32 bits; NC = 2 is for partitions with k <= PAIR_KMAX.
+    template <int NC, bool VALUES>
+    CLX_HD bool codes8(int32_t (&e)[8]) {
         bool bad = false;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t hi = hd_fsl(W0, W1, o);
-            bad = bad || hi < thr;
-            const uint32_t m = hd_msb(hi);             // terminator at bit m: unary quotient q = 31 - m
-            const uint32_t v = hi >> ((m - k) & 31u);  // K + r
-            const uint32_t u = m * Kneg + (v + K30);   // (q << k) | r = (30 - m) * K + v
-            // rice_to_signed (src/subframe.rs:157-170): (u >> 1) ^ -(u & 1) = (u >> 1) + (-(u & 1)) * u, wrapping
-            e[i] = (int32_t)((u >> 1) + hd_neg_lsb(u) * u);
-            const uint32_t on = o + c32k - m;          // o + q + 1 + k
-            if ((on ^ o) >> 5) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
+        for (int i = 0; i < 8; i += NC) {
+            uint32_t x = hd_fsl(W0, W1, o);
+            uint32_t s = 0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const uint32_t m = hd_msb(x);   // terminator at bit m: unary quotient q = 31 - m
+                const uint32_t l = c32k - m;    // q + 1 + k
+                if (VALUES) e[i + j] = code_value(x, m);
+                s += l;
+                if (j + 1 < NC) x = hd_fsl(x, 0u, l);
+            }
+            bad = bad || s > 32u;
+            const uint32_t on = o + s;
+            if ((on ^ o) & 32u) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
             o = on;
         }
-        if (bad) { o = o0; need_seek = true; return false; }
+        return bad;
+    }
+    template <bool VALUES>
+    CLX_HD bool codes8_by_cap(int32_t (&e)[8]) {
+        return ncap == 2 ? codes8<2, VALUES>(e) : codes8<1, VALUES>(e);
+    }
+    // The group, by the form the partition allows; precondition n_fast != 0.  On failure the cursor is put back
+    // and the fast path closed: the caller then takes the eight codes one by one.  (A quad or pair that fails
+    // only because its codes are too long TOGETHER is retried one form down first.)
+    template <bool VALUES>
+    CLX_HD bool fast_group_t(int32_t (&e)[8]) {
+        if (!io.prefetch_group(o)) { n_fast = 0; return false; }
+        const uint32_t o0 = o, w0 = W0, w1 = W1, w2 = W2;
+        bool bad = codes8_by_cap<VALUES>(e);
+        if (bad && ncap > 1) {  // once more, one code per refill: needs the window back
+            o = o0; W0 = w0; W1 = w1; W2 = w2;
+            io.seek_next((o0 >> 5) + 3);
+            bad = codes8<1, VALUES>(e);
+        }
+        if (bad) { o = o0; n_fast = 0; return false; }
         n_left -= 8;
+        n_fast--;
         return true;
     }
-    // ---- the same eight codes, positions only ----
-    CLX_HD bool skip_group() {
-        if (!io.prefetch_group(o)) { need_seek = true; return false; }
+    CLX_HD bool fast_group(int32_t (&e)[8]) { return fast_group_t<true>(e); }
+    CLX_HD bool skip_group() {  // the same eight codes, positions only
+        int32_t unused[8];
+        return fast_group_t<false>(unused);
+    }
+    // The same group SPECULATIVELY and branch-free, whatever the lane's state (every memory access it makes is
+    // safe in any state): the caller learns afterwards whether the residuals are real.  This lets the caller put
+    // the group in one basic block with independent work (the previous group's prediction), so that the two
+    // dependency chains — and the ALU-heavy bit scan and the multiply-add-heavy recurrence — interleave.
+    // NC may be at most the `ncap` of every lane that is on the fast path.
+    template <int NC>
+    CLX_HD bool spec_group(int32_t (&e)[8]) {
+        const bool was_fast = n_fast != 0;
+        const bool ring_ok = io.prefetch_group(o);
         const uint32_t o0 = o;
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t hi = hd_fsl(W0, W1, o);
-            bad = bad || hi < thr;
-            const uint32_t on = o + c32k - hd_msb(hi);
-            if ((on ^ o) >> 5) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
-            o = on;
-        }
-        if (bad) { o = o0; need_seek = true; return false; }
-        n_left -= 8;
-        return true;
+        const bool bad = codes8<NC, true>(e);
+        const bool good = was_fast && ring_ok && !bad;
+        o = good ? o : o0;
+        n_left = good ? n_left - 8 : n_left;
+        n_fast = good ? n_fast - 1 : 0u;
+        return good;
     }
     // ---- one Rice code of any shape; precondition n_left > 0 ----
     CLX_HD int32_t slow_code() {
-        need_seek = true;
+        n_fast = 0;
         uint32_t q = 0;
         uint32_t v;
         for (;;) {
@@ -264,19 +322,14 @@ struct IndexLane {
         bs = d.block_size; nch = d.n_channels; ca = d.channel_assignment; fbps = d.bits_per_sample;
         byte_len = d.byte_len;
         bit0 = (uint32_t)(d.byte_offset & 15) * 8;
-        rc.limit = bit0 + d.byte_len * 8;
-        rc.o = bit0 + (uint32_t)d.header_len * 8;
-        rc.W0 = rc.W1 = rc.W2 = 0;
-        rc.n_left = 0; rc.parts_left = 0; rc.per = 0; rc.order = 0; rc.pbits = 4;
-        rc.k = 0; rc.Kneg = 0xffffffffu; rc.K30 = 30; rc.c32k = 32; rc.thr = 1;
-        rc.ok = true; rc.need_seek = true; rc.first_part = false;
+        rc.reset(bit0 + (uint32_t)d.header_len * 8, bit0 + d.byte_len * 8);
         mode = SEQ_SUBFRAME; ch = 0; slow_budget = 0;
         if (nch > max_channels || nch == 0 || fbps == 0) fail();
     }
     CLX_HD void fail() { rc.fail(); mode = SEQ_DONE; }
     CLX_HD bool ok() const { return rc.ok; }
     CLX_HD bool done() const { return mode == SEQ_DONE; }
-    CLX_HD bool fast_ready() const { return mode == SEQ_RUN && slow_budget == 0 && rc.group_ready(); }
+    CLX_HD bool fast_ready() const { return mode == SEQ_RUN && rc.n_fast != 0; }
     CLX_HD void fast_group() {
         if (!rc.skip_group()) { slow_budget = 8; return; }
         if (rc.n_left == 0 && rc.parts_left == 0 && rc.ok) end_of_body();
@@ -392,7 +445,7 @@ struct IndexLane {
             end_of_body();
             return;
         }
-        if (rc.n_left >= 8) { io.ensure(o); rc.window_seek(); }
+        if (rc.n_left >= 8) rc.window_seek();
     }
 
     // everything that is not a fast group
@@ -404,7 +457,7 @@ struct IndexLane {
             end_of_body();
             return;
         }
-        if (slow_budget == 0 && rc.need_seek && rc.n_left >= 8) { rc.io.ensure(rc.o); rc.window_seek(); return; }  // next: a fast group
+        if (slow_budget == 0 && rc.n_left >= 8) { rc.window_seek(); return; }  // next step: a fast group
         rc.slow_code();
         if (slow_budget) slow_budget--;
         if (!rc.ok) { fail(); return; }
@@ -422,27 +475,24 @@ struct SubLane {
 
     // `limit`: first bit past the frame's bytes; the cursor starts at sp.res_bit
     CLX_HD void init(const SeqParams& sp, uint32_t bs, uint32_t limit) {
-        rc.limit = limit;
-        rc.o = sp.res_bit;
-        rc.W0 = rc.W1 = rc.W2 = 0;
-        rc.n_left = 0; rc.parts_left = 0; rc.per = 0; rc.order = 0; rc.pbits = 4;
-        rc.k = 0; rc.Kneg = 0xffffffffu; rc.K30 = 30; rc.c32k = 32; rc.thr = 1;
-        rc.ok = true; rc.need_seek = true; rc.first_part = false;
+        rc.reset(sp.res_bit, limit);
         kind = (uint32_t)sp.kind;
         sfbps = sp.sfbps;
         if (kind == SUB_PREDICTED) rc.residual_header(bs, (uint32_t)sp.order);
     }
     CLX_HD void init_idle() {
-        rc.limit = 0; rc.o = 0; rc.W0 = rc.W1 = rc.W2 = 0;
-        rc.n_left = 0; rc.parts_left = 0; rc.per = 0; rc.order = 0; rc.pbits = 4;
-        rc.k = 0; rc.Kneg = 0xffffffffu; rc.K30 = 30; rc.c32k = 32; rc.thr = 1;
-        rc.ok = true; rc.need_seek = true; rc.first_part = false;
+        rc.reset(0, 0);
         kind = SUB_CONSTANT; sfbps = 1;
     }
     CLX_HD bool ok() const { return rc.ok; }
+    // A group of eight residuals: `if (!fast()) prepare(); if (fast()) got = fast_group(e); if (!got) eight next()`.
+    CLX_HD bool fast() const { return rc.n_fast != 0; }
     CLX_HD void prepare() { if (kind == SUB_PREDICTED) rc.prepare(); }
-    CLX_HD bool group_ready() const { return kind == SUB_PREDICTED && rc.group_ready(); }
     CLX_HD bool fast_group(int32_t (&e)[8]) { return rc.fast_group(e); }
+    // codes per refill spec_group may use for this lane (a lane off the fast path does not care)
+    CLX_HD uint32_t spec_cap() const { return rc.n_fast == 0 ? 2u : rc.ncap; }
+    template <int NC>
+    CLX_HD bool spec_group(int32_t (&e)[8]) { return rc.template spec_group<NC>(e); }
     // one residual through the slow path, whatever the subframe's kind; 0 once the lane has failed
     CLX_HD int32_t next() {
         if (kind == SUB_CONSTANT || !rc.ok) return 0;

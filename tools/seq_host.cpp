@@ -34,7 +34,8 @@ struct HostIO {
 }  // namespace
 
 // head_pad: extra groups of eight samples taken one by one before the grouped part starts, as happens
-// to a lane whose warp holds a subframe of a higher order.  stats[0] += fast groups, stats[1] += slow codes.
+// to a lane whose warp holds a subframe of a higher order; odd values also make the speculative group take one
+// code per window refill throughout (as in a warp where some lane's Rice parameter is above PAIR_KMAX).  stats[0] += fast groups, stats[1] += slow codes.
 extern "C" int seq_host_decode(const uint8_t* bytes, uint64_t nbytes, const clx_frame_desc* descs, uint32_t n,
                                uint32_t head_pad, int32_t* out, clx_frame_result* results, uint64_t* stats) {
     uint32_t max_ch = 1;
@@ -91,17 +92,47 @@ extern "C" int seq_host_decode(const uint8_t* bytes, uint64_t nbytes, const clx_
                 }
             };
             guarded(0, head_end);
-            for (uint32_t t = head_end; t < bulk_end; t += 8) {
-                int32_t r[8];
-                bool got = false;
-                L.prepare();
-                if (L.group_ready()) got = L.fast_group(r);
-                if (got) { if (stats) stats[0]++; }
-                else {
-                    for (int i = 0; i < 8; i++) r[i] = L.next();
-                    if (stats) stats[1] += 8;
+            if (bulk_end > head_end) {
+                // the kernel's software pipeline: a trip consumes the residuals the previous trip produced and
+                // produces the next group speculatively (spec_group), falling back to the ordinary route
+                int32_t ra[8], rb[8];
+                auto produce = [&](int32_t (&dst)[8], bool try_fast) {
+                    bool got = false;
+                    if (try_fast) {
+                        if (!L.fast()) L.prepare();
+                        if (L.fast()) got = L.fast_group(dst);
+                    }
+                    if (got) { if (stats) stats[0]++; }
+                    else {
+                        for (int i = 0; i < 8; i++) dst[i] = L.next();
+                        if (stats) stats[1] += 8;
+                    }
+                };
+                auto consume = [&](const int32_t (&r)[8], uint32_t t) {
+                    for (uint32_t i = 0; i < 8; i++) predict(t + i, r[i]);
+                };
+                auto step = [&](const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
+                    // the warp takes the smallest number of codes per refill any of its lanes allows: emulate
+                    // neighbours with larger Rice parameters through head_pad
+                    uint32_t nc = L.spec_cap();
+                    if ((head_pad & 1u) && nc > 1) nc >>= 1;
+                    const bool good = nc == 2 ? L.spec_group<2>(prod) : L.spec_group<1>(prod);
+                    consume(cons, t);
+                    if (good) { if (stats) stats[0]++; }
+                    else produce(prod, true);
+                };
+                produce(ra, true);
+                uint32_t t = head_end;
+                while (t + 16 < bulk_end) {
+                    step(ra, rb, t);
+                    step(rb, ra, t + 8);
+                    t += 16;
                 }
-                for (uint32_t i = 0; i < 8; i++) predict(t + i, r[i]);
+                if (t + 8 < bulk_end) {
+                    step(ra, rb, t);
+                    t += 8;
+                    consume(rb, t);
+                } else consume(ra, t);
             }
             guarded(bulk_end, bs);
             const uint32_t end_bit = L.finish();
