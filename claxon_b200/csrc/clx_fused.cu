@@ -134,6 +134,9 @@ index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const
         L.rc.ok = true;
     }
     while (__any_sync(0xffffffffu, !L.done())) {
+        // the steady state, a tight loop of its own: every lane of the warp steps over eight codes
+        while (__all_sync(0xffffffffu, L.fast_ready())) L.fast_group();
+        // anything else (headers, partition switches, long codes, lanes that are done): one mixed step
         if (L.fast_ready()) L.fast_group();
         else if (!L.done()) L.slow_step();
         __syncwarp();

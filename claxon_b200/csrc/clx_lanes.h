@@ -86,6 +86,15 @@ CLX_HD uint32_t hd_fsl(uint32_t hi, uint32_t lo, uint32_t n) {
     return n ? (hi << n) | (lo >> (32 - n)) : hi;
 #endif
 }
+// lower 32 bits of (hi:lo) >> (n & 31)
+CLX_HD uint32_t hd_fsr(uint32_t hi, uint32_t lo, uint32_t n) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, n);
+#else
+    n &= 31;
+    return n ? (lo >> n) | (hi << (32 - n)) : lo;
+#endif
+}
 CLX_HD uint32_t hd_bswap(uint32_t v) {
 #ifdef __CUDA_ARCH__
     return __byte_perm(v, 0, 0x0123);
@@ -124,7 +133,7 @@ struct RiceCursor {
     // waits for the shared-memory load that produced it.
     uint32_t W0, W1, W2;
     uint32_t n_left, parts_left, per, order, pbits;
-    uint32_t k, Kneg, K30, c32k;
+    uint32_t k, Kneg, K30;
     uint32_t ncap;        // codes per window refill this partition allows: 2 or 1
     uint32_t n_fast;      // groups of eight codes the fast path may take before anything else has to happen
     bool ok, first_part;
@@ -133,7 +142,7 @@ struct RiceCursor {
         o = start_bit; limit = limit_bit;
         W0 = W1 = W2 = 0;
         n_left = 0; parts_left = 0; per = 0; order = 0; pbits = 4;
-        k = 0; Kneg = 0xffffffffu; K30 = 30; c32k = 32; ncap = 1;
+        k = 0; Kneg = 0xffffffffu; K30 = 30; ncap = 1;
         n_fast = 0;
         ok = true; first_part = false;
     }
@@ -179,9 +188,8 @@ struct RiceCursor {
         first_part = false;
         parts_left--;
         const uint32_t K = 1u << k;
-        K30 = 30u * K;
+        K30 = (30u - k) * K;
         Kneg = 0u - K;
-        c32k = 32u + k;
         ncap = k <= PAIR_KMAX ? 2u : 1u;
         if (o > limit) fail();
     }
@@ -201,11 +209,11 @@ struct RiceCursor {
         if (ok && n_left >= 8) window_seek();
     }
 
-    // (q << k) | r of the code whose 32-bit window is `hi` with its terminator at bit m, then rice_to_signed
-    // (src/subframe.rs:157-170): (u >> 1) ^ -(u & 1).
-    CLX_HD int32_t code_value(uint32_t hi, uint32_t m) const {
-        const uint32_t v = hi >> ((m - k) & 31u);  // K + r
-        const uint32_t u = m * Kneg + (v + K30);   // (q << k) | r = (30 - m) * K + v,  q = 31 - m
+    // (q << k) | r of the code whose 32-bit window is `hi` with its terminator at bit m = sh + k, then
+    // rice_to_signed (src/subframe.rs:157-170): (u >> 1) ^ -(u & 1).
+    CLX_HD int32_t code_value(uint32_t hi, uint32_t sh) const {
+        const uint32_t v = hi >> (sh & 31u);      // K + r
+        const uint32_t u = sh * Kneg + (v + K30); // (q << k) | r = (30 - k - sh) * K + v,  q = 31 - k - sh
         return (int32_t)((u >> 1) ^ hd_neg_lsb(u));
     }
 
@@ -213,8 +221,8 @@ struct RiceCursor {
     // NC codes share one 32-bit window and one refill test: the window of the next code is the previous one's
     // shifted left by its length (zeros come in at the bottom), which is all it needs as long as the NC codes
     // TOGETHER are at most 32 bits long.  A code that does not fit — its terminator or its remainder beyond the
-    // window, or no terminator at all (bfind of 0 is 0xffffffff) — makes the sum of the lengths exceed 32, so
-    // that one comparison per refill covers everything; what was decoded after such a code is meaningless
+    // window, or no terminator at all (bfind of 0 is 0xffffffff) — makes the sum of the lengths exceed 32 (for one
+    // code alone: makes sh negative), so that one comparison per refill covers everything; what was decoded after such a code is meaningless
     // (but harmless: every shared-memory address is masked into the lane's ring) and `bad` is returned.
     // NC = 1 takes any code of up to 32 bits; NC = 2 is for partitions with k <= PAIR_KMAX.
     template <int NC, bool VALUES>
@@ -223,17 +231,16 @@ struct RiceCursor {
 #pragma unroll
         for (int i = 0; i < 8; i += NC) {
             uint32_t x = hd_fsl(W0, W1, o);
-            uint32_t s = 0;
+            uint32_t t = 0;  // sum of sh = m - k over the NC codes; a code is 32 - sh bits long
 #pragma unroll
             for (int j = 0; j < NC; j++) {
-                const uint32_t m = hd_msb(x);   // terminator at bit m: unary quotient q = 31 - m
-                const uint32_t l = c32k - m;    // q + 1 + k
-                if (VALUES) e[i + j] = code_value(x, m);
-                s += l;
-                if (j + 1 < NC) x = hd_fsl(x, 0u, l);
+                const uint32_t sh = hd_msb(x) - k;  // terminator at bit m = sh + k (sh < 0: it does not fit)
+                if (VALUES) e[i + j] = code_value(x, sh);
+                t += sh;
+                if (j + 1 < NC) x = hd_fsr(x, 0u, sh);  // x << (32 - sh): the next code's window
             }
-            bad = bad || s > 32u;
-            const uint32_t on = o + s;
+            bad = bad || (int32_t)t < 32 * (NC - 1);  // the NC codes are longer than 32 bits together
+            const uint32_t on = o - t + 32u * NC;
             if ((on ^ o) & 32u) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
             o = on;
         }
