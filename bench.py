@@ -4,32 +4,44 @@
 Metric (BASELINE.json): Msamples/s decoded, bit-exact, samples = sum(block_size * channels).
 Workload at N=1: BASELINE.json configs[1] ("c2"): batch of 1024 synthetic stereo 16-bit frames,
 block size 4096, LPC order 8, Rice parameter 4, mid/side.  One *step* = one pass of the hot path
-(`FrameReader::read_next_or_eof` for every frame of the batch) over one such batch.
+(`FrameReader::read_next_or_eof` for every frame of the batch) over one such batch ("unit").
 
-  value  — kernel-only throughput, inputs resident in HBM.  Steps are issued round-robin over
-           `--inflight` distinct device-resident batches (combined footprint > L2, so no step
-           finds its inputs or outputs in L2) on `--streams` CUDA streams, i.e. many batches in
-           flight: the steady-state regime of a decode service.  A lone 1024-frame batch is
-           latency-bound by the serial LPC recurrence and by the sequential
-           window chain of the entropy decode; its figure is reported next to it as `single_batch`.
-           A step takes ~15 us, so `--steps K` alone would be a sub-millisecond window: the timed
-           region is `repeats` x K steps issued back to back (no drain in between; `repeats` is
-           chosen so that the region holds >= --min-steps steps), it is measured three times and
-           the median region is reported; ms_per_step = region / (repeats * K).  Every batch's CUDA
-           graph is instantiated when the batch is created and every batch is decoded once before
-           anything is timed, whatever --warmup says.
+  value  — kernel-only throughput, inputs resident in HBM.  The job is a list of units (distinct
+           batches: combined footprint > L2, so no step finds its inputs or outputs in L2); the list is
+           partitioned over the ranks by `claxon_b200.shard.plan_shards` (contiguous ranges balanced on
+           algorithmic bytes, no data-path collective: frames are independent, reference
+           src/frame.rs:603-605) and every rank cycles its units over `--streams` CUDA streams, i.e.
+           many batches in flight: the steady-state regime of a decode service.  `--scaling weak`
+           (default): `--inflight` units per rank; `--scaling strong`: a fixed corpus of `--units`
+           units split over the ranks.  A lone 1024-frame batch is latency-bound by the serial LPC
+           recurrence and the sequential Rice walk; its figure is reported next to
+           it as `single_batch`.  A step takes ~15 us, so `--steps K` alone would be a sub-millisecond
+           window: the timed region is `repeats` x K steps issued back to back (no drain in between;
+           `repeats` is chosen so that the region holds >= --min-steps steps), it is measured
+           `--regions` times and the median region is reported; ms_per_step = region / (repeats * K).
+           Every batch's CUDA graph is instantiated when the batch is created and every batch is
+           decoded once before anything is timed, whatever --warmup says.
   e2e    — same metric through the public host-buffer call (`clx_decode_frames`): per step the
-           compressed frames go pinned-host -> device and the full planar i32 PCM comes back.
+           compressed frames go pinned-host -> device and the full planar i32 PCM comes back.  The call
+           is synchronous; `--e2e-callers` host threads (default 2, each with its own context and pinned
+           buffers, as the worker threads of a decode service) call it concurrently, so that one call's
+           copy-out overlaps the next one's copy-in and kernels; `e2e.one_caller` is the same with a
+           single caller.
+           `e2e_i16`: the same call in the interleaved 16-bit output mode (what a WAV writer or the
+           STREAMINFO MD5 consumes; half the bytes over PCIe) — a different metric row, reported apart.
   roofline — HBM: algorithmic bytes (frame bytes read once + planar i32 written once) / device
            time, against the measured copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline — the CPU oracle (a C restatement of claxon; kind "port") on all host cores.
+  workloads — at N=1, short measurements of BASELINE.json's other configurations (c3, c4, c5) by the
+           same method, bit-exactness checked against the generator's PCM.
 
 `--impl reference` times that CPU port alone, same config/metric (the reference itself is Rust and
-cannot be built in this image: no rustc).
+cannot be built in this image or on the GPU box: no rustc / cargo on either).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -43,6 +55,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 METRIC = "Msamples/s decoded (bit-exact)"
+
+# frames per unit (one device-resident batch) of each workload, and units of the whole corpus (strong scaling)
+UNIT_FRAMES = {"c2": 1024, "c2-indep": 1024, "c3": 8192, "c4": 1100, "c5": 256}
+CORPUS_UNITS = {"c2": 64, "c2-indep": 64, "c3": 8, "c4": 100, "c5": 16}
 
 
 def env_int(name, default):
@@ -121,7 +137,7 @@ def measured_peak_gbs():
 
 
 def load_traffic():
-    """dram bytes per launch of the decode kernel from the committed ncu capture, if any."""
+    """dram bytes per launch of the decode kernels from the committed ncu capture, if any."""
     p = os.path.join(HERE, "profiles", "traffic.json")
     try:
         with open(p) as f:
@@ -142,13 +158,33 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_single_thread_rate(batch, min_seconds=1.0):
-    """claxon is single-threaded: the same port on ONE host thread; None on any problem."""
+def _numa_of(local):
+    import torch
+    p = torch.cuda.get_device_properties(local)
+    with open(f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node") as f:
+        return int(f.read())
+
+
+def pin_to_gpu_numa_node(local, world):
+    """Keeps this rank's host threads (CRC pool, staging copies) on the NUMA node its GPU hangs off, and
+    returns (threads this rank may use, note).  Ranks that share a node split its CPUs between them."""
+    total = os.cpu_count() or 1
     try:
-        v, _, _ = cpu_decode_rate(batch, 1, min_seconds)
-        return v
-    except Exception:
-        return None
+        node = _numa_of(local)
+        if node < 0:
+            raise ValueError("no NUMA node recorded")
+        cpus = []
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus += list(range(int(lo), int(hi or lo) + 1))
+        peers = [r for r in range(world) if _numa_of(r) == node]
+        mine = cpus[peers.index(local)::len(peers)] if local in peers else cpus
+        os.sched_setaffinity(0, mine)
+        return len(mine), f"pinned to NUMA node {node}: {len(mine)} of its {len(cpus)} CPUs"
+    except Exception as e:  # no sysfs entry, no permission ...: split the machine evenly instead
+        n = max(1, total // max(1, world))
+        return n, f"not pinned ({type(e).__name__}); {n} threads per rank"
 
 
 def cpu_decode_rate(batch, threads, min_seconds):
@@ -167,6 +203,94 @@ def cpu_decode_rate(batch, threads, min_seconds):
     return batch.n_samples * reps / dt / 1e6, reps, dt
 
 
+def describe(workload, cfg):
+    return (f"{workload}: {cfg.n_frames} frames x {cfg.n_channels}ch x bs{cfg.block_size}, {cfg.bps}-bit, "
+            f"LPC order {cfg.lpc_min_order}-{cfg.lpc_max_order}, Rice k={cfg.rice_mode}, stereo_mode={cfg.stereo_mode}")
+
+
+def unit_config(synth, workload, unit_index, frames=None):
+    """Unit `unit_index` of a workload: same shape, its own content (frame i of a unit depends on seed + i only)."""
+    cfg = synth.workload_config(workload, frames or UNIT_FRAMES[workload])
+    cfg.seed = cfg.seed + 1000003 * unit_index
+    return cfg
+
+
+class Job:
+    """This rank's share of a list of units, resident on the device."""
+
+    def __init__(self, cb, synth, ctx, workload, unit_ids, frames=None, keep_host=2):
+        self.batches, self.host = [], []
+        self.unit_alg, self.unit_samples = [], []
+        for j, u in enumerate(unit_ids):
+            b = synth.generate(unit_config(synth, workload, u, frames))
+            descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
+            self.batches.append(ctx.upload(b.data, descs, out_elems))
+            if j < keep_host:
+                self.host.append((b, descs, out_elems))
+            self.unit_alg.append(int(b.data.size) + 4 * b.n_samples)
+            self.unit_samples.append(b.n_samples)
+        self.alg_bytes = sum(self.unit_alg)
+        self.n_samples = sum(self.unit_samples)
+
+    def exact(self, idx=0):
+        """The timed kernels' output of unit `idx` equals the generator's PCM bit for bit (and every status is OK)."""
+        bt = self.batches[idx]
+        bt.decode(0)
+        out, res = bt.read()
+        b, d, out_elems = self.host[idx]
+        if not bool((res["status"] == 0).all()):
+            return False
+        if out_elems == b.n_samples:
+            return hashlib.sha1(out[:out_elems].tobytes()).digest() == hashlib.sha1(b.pcm.tobytes()).digest()
+        for i in range(b.n_frames):
+            o = int(d[i]["out_offset"]); lo, hi = int(b.pcm_offsets[i]), int(b.pcm_offsets[i + 1])
+            if not np.array_equal(out[o:o + hi - lo], b.pcm[lo:hi]):
+                return False
+        return True
+
+    def steady(self, ctx, steps, streams, regions, sync=None):
+        """`regions` timed regions of `steps` steps each (round-robin over this rank's units); device ms each."""
+        n = len(self.batches)
+        ctx.run_steps(self.batches, max(n, 3), streams)  # every batch once, at least
+        out = []
+        for _ in range(max(1, regions)):
+            if sync:
+                sync()
+            out.append(ctx.run_steps(self.batches, steps, streams))
+        return out
+
+    def per_steps(self, steps):
+        """(samples, algorithmic bytes) that `steps` round-robin steps cover."""
+        n = len(self.batches)
+        full, rem = divmod(steps, n)
+        return (full * self.n_samples + sum(self.unit_samples[:rem]), full * self.alg_bytes + sum(self.unit_alg[:rem]))
+
+    def close(self):
+        for b in self.batches:
+            b.close()
+        self.batches = []
+
+
+def short_line(cb, synth, ctx, workload, n_units, streams, min_ms=40.0):
+    """A short steady-state measurement of another BASELINE.json configuration on this GPU."""
+    t0 = time.time()
+    job = Job(cb, synth, ctx, workload, list(range(n_units)), keep_host=1)
+    exact = job.exact(0)
+    one = ctx.run_steps(job.batches, n_units, streams) / n_units  # ms per step, rough
+    steps = max(n_units * 2, int(min_ms / max(one, 1e-3)))
+    ms = float(np.median(job.steady(ctx, steps, streams, 3)))
+    samples, alg = job.per_steps(steps)
+    peak, _ = measured_peak_gbs()
+    cfg = unit_config(synth, workload, 0)
+    line = {"config": describe(workload, cfg), "frames_per_step": UNIT_FRAMES[workload], "units_in_flight": n_units,
+            "footprint_mb": round(job.alg_bytes / 1e6), "steps": steps, "ms_per_step": ms / steps,
+            "value": samples / (ms / 1e3) / 1e6, "unit": "Msamples/s", "bit_exact": bool(exact),
+            "bytes_per_sample": alg / samples, "roofline_frac": alg / (ms / 1e3) / 1e9 / peak}
+    job.close()
+    line["wall_s"] = round(time.time() - t0, 1)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,12 +299,16 @@ def main():
     ap.add_argument("--regions", type=int, default=3, help="timed regions; the median is reported")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="claxon_b200", choices=["claxon_b200", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--frames", type=int, default=None, help="override frames per batch")
-    ap.add_argument("--inflight", type=int, default=64, help="distinct device-resident batches cycled")
+    ap.add_argument("--workload", default="c2", choices=sorted(UNIT_FRAMES))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=None, help="override frames per unit")
+    ap.add_argument("--inflight", type=int, default=None, help="weak scaling: units per rank (default: the workload's corpus)")
+    ap.add_argument("--units", type=int, default=None, help="strong scaling: units of the whole corpus")
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--e2e-callers", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the short c3 / c4 / c5 lines at N=1")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -188,12 +316,8 @@ def main():
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "64")
     from claxon_b200 import synth
 
-    cfg = synth.workload_config(args.workload, args.frames)
-    cfg.seed += 7919 * rank  # weak scaling: every rank decodes its own batch of the same shape
-    config = {"workload": f"{args.workload}: {cfg.n_frames} frames x {cfg.n_channels}ch x bs{cfg.block_size}, "
-                          f"{cfg.bps}-bit, LPC order {cfg.lpc_min_order}-{cfg.lpc_max_order}, "
-                          f"Rice k={cfg.rice_mode}, stereo_mode={cfg.stereo_mode}",
-              "frames_per_step": cfg.n_frames, "parallelism": f"frames sharded over {world} GPU(s), no collective"}
+    cfg = unit_config(synth, args.workload, 0, args.frames)
+    config = {"workload": describe(args.workload, cfg), "frames_per_step": cfg.n_frames}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -215,18 +339,19 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32/int64",
             "data": "synthetic", "config": config, "bit_exact": bool(ok),
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                              "sample": f"{args.steps} x full {args.workload} batch ({batch.n_samples} samples)",
                              "note": "C restatement of claxon v0.4.3 (oracle/), frames sharded over threads; "
-                                     "claxon itself is Rust and cannot be built here (no rustc)"},
+                                     "claxon itself is Rust and cannot be built here (no rustc / cargo)"},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
 
     # ------------------------------------------------------------------ GPU arm
     import claxon_b200 as cb
+    from claxon_b200 import shard
 
     dist = None
     if world > 1:
@@ -243,136 +368,181 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if dist is None:
             return x
         import torch
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    ctx = cb.Context(device=local, n_streams=max(2, args.streams))
-    e2e_ctx = cb.Context(device=local, n_streams=8)  # the host-buffer call pipelines up to 8 chunks per batch
-    # distinct batches (different content, same shape) so that the working set exceeds L2
-    n_distinct = max(1, args.inflight)
-    batches, host = [], []
-    alg_bytes = None
-    for i in range(n_distinct):
-        c = synth.workload_config(args.workload, args.frames)
-        c.seed = cfg.seed + 1000003 * i
-        b = synth.generate(c)
-        descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
-        batches.append(ctx.upload(b.data, descs, out_elems))
-        if i < 2:
-            host.append((b, descs, out_elems))
-        if alg_bytes is None:
-            alg_bytes = int(b.data.size) + 4 * b.n_samples
-            n_samples = b.n_samples
-            in_bytes = int(b.data.size)
-    footprint_mb = n_distinct * (alg_bytes) / 1e6
-    config.update({"inflight_batches": n_distinct, "streams": args.streams,
-                   "l2": f"steps cycle over {n_distinct} distinct batches, footprint {footprint_mb:.0f} MB > 126 MB L2"})
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX) if dist is not None else x
 
-    # correctness gate: the timed kernels' output must equal the expected PCM bit for bit
-    batches[0].decode(0)
-    out, res = batches[0].read()
-    b0, d0, _ = host[0]
-    exact = bool((res["status"] == 0).all())
-    for i in range(b0.n_frames):
-        o = int(d0[i]["out_offset"]); lo, hi = int(b0.pcm_offsets[i]), int(b0.pcm_offsets[i + 1])
-        if not np.array_equal(out[o:o + hi - lo], b0.pcm[lo:hi]):
-            exact = False
-            break
+    def sum_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.SUM) if dist is not None else x
 
-    # ---- single-batch (latency regime): one batch, serialised steps, flushing nothing (reported only)
-    for _ in range(3):
-        batches[0].decode(0); batches[0].sync()
-    single = []
-    for i in range(10):
-        bt = batches[(i + 1) % n_distinct]
-        bt.decode(0); bt.sync()
-        single.append(bt.kernel_ms())
-    single_ms = float(np.median(single))
+    host_threads, pin_note = pin_to_gpu_numa_node(local, world)
+    host_threads = max(1, min(32, host_threads))
+    ctx = cb.Context(device=local, n_streams=max(2, args.streams), host_threads=host_threads)
 
-    # ---- steady state: repeats x K steps back to back, several batches in flight
-    repeats = max(1, -(-args.min_steps // max(1, args.steps)))
-    timed_steps = repeats * args.steps
+    # ---- the job: a list of units, partitioned over the ranks by plan_shards (equal shapes: equal shares)
+    if args.scaling == "weak":
+        n_units = (args.inflight or CORPUS_UNITS[args.workload]) * world
+    else:
+        n_units = args.units or CORPUS_UNITS[args.workload]
+    unit_descs = np.zeros(n_units, dtype=cb.DESC_DTYPE)  # one pseudo-frame per unit: every unit costs the same
+    unit_descs["byte_len"] = 1
+    unit_descs["n_channels"] = 1
+    unit_descs["block_size"] = 1
+    lo, hi = shard.plan_shards(unit_descs, world)[rank]
+    job = Job(cb, synth, ctx, args.workload, list(range(lo, hi)), args.frames)
+    n_mine = hi - lo
+    config.update({"parallelism": f"{n_units} units over {world} GPU(s) by plan_shards, no collective on the data path",
+                   "units": n_units, "units_this_rank": n_mine, "streams": args.streams, "host": pin_note,
+                   "l2": f"steps cycle over {n_mine} distinct batches per GPU, footprint {job.alg_bytes / 1e6:.0f} MB > 126 MB L2"})
+
+    exact = job.exact(0) if n_mine else True
+
+    # ---- single-batch (latency regime): one batch, serialised steps (reported only)
+    single_ms = None
+    if n_mine:
+        for _ in range(3):
+            job.batches[0].decode(0); job.batches[0].sync()
+        single = []
+        for i in range(10):
+            bt = job.batches[(i + 1) % n_mine]
+            bt.decode(0); bt.sync()
+            single.append(bt.kernel_ms())
+        single_ms = float(np.median(single))
+
+    # ---- steady state
+    if args.scaling == "weak":
+        repeats = max(1, -(-args.min_steps // max(1, args.steps)))
+        my_steps = repeats * args.steps        # per rank; the job's steps are world x that
+        timed_steps = my_steps * world
+    else:  # a step = one unit of the corpus; a region = `repeats` passes over the whole corpus
+        repeats = max(1, -(-max(args.min_steps, args.steps) // n_units))
+        my_steps = repeats * n_mine
+        timed_steps = repeats * n_units
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.run_steps(batches, max(n_distinct, max(args.warmup, 3)), args.streams)  # every batch once, at least
-    barrier()
-    region_ms = []
-    gpu_launches = 0
+    launches0 = ctx.launch_count
     t_wall0 = time.time()
-    for _ in range(max(1, args.regions)):
-        launches1 = ctx.launch_count
-        r_ms = ctx.run_steps(batches, timed_steps, args.streams)
-        gpu_launches = ctx.launch_count - launches1
-        barrier()
-        region_ms.append(max_over_ranks(r_ms))
+    regions = [max_over_ranks(r) for r in (job.steady(ctx, my_steps, args.streams, args.regions, barrier) if n_mine
+                                            else [0.0] * max(1, args.regions))]
     t_wall1 = time.time()
+    launches_all = ctx.launch_count - launches0
+    barrier()
     clocks = sampler.stop(t_wall0, t_wall1)
-    ms = float(np.median(region_ms))
-    value = n_samples * timed_steps * world / (ms / 1e3) / 1e6
-
+    ms = float(np.median(regions))
+    my_samples, my_alg = job.per_steps(my_steps) if n_mine else (0, 0)
+    gpu_launches = int(round(launches_all * my_steps / (my_steps * max(1, args.regions) + max(n_mine, 3)))) if n_mine else 0
+    tot_samples, tot_alg = sum_over_ranks(my_samples), sum_over_ranks(my_alg)
+    value = tot_samples / (ms / 1e3) / 1e6
     peak, peak_src = measured_peak_gbs()
-    achieved = alg_bytes * timed_steps / (ms / 1e3) / 1e9
+    achieved = tot_alg / world / (ms / 1e3) / 1e9  # per GPU
     traffic = load_traffic()
 
     # ---- end to end through the host-buffer call, pinned memory
-    e2e_steps = args.e2e_steps or max(5, min(args.steps, 30))
-    hb, hd, hout_elems = host[0]
-    ectx = e2e_ctx
-    p_bytes = ctx.host_alloc(int(hb.data.size) + 64)
-    p_bytes[: hb.data.size] = hb.data
-    p_out = ctx.host_alloc(4 * hout_elems + 64)
-    out_view = p_out[: 4 * hout_elems].view(np.int32)
-    results = np.zeros(hd.size, dtype=cb.RESULT_DTYPE)
-    for _ in range(3):
-        ectx.decode_frames_raw(p_bytes.ctypes.data, hb.data.size, hd.ctypes.data, hd.size, p_out.ctypes.data,
-                               hout_elems, results.ctypes.data)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ectx.decode_frames_raw(p_bytes.ctypes.data, hb.data.size, hd.ctypes.data, hd.size, p_out.ctypes.data,
-                               hout_elems, results.ctypes.data)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_ok = bool((results["status"] == 0).all())
-    for i in range(0, hb.n_frames, max(1, hb.n_frames // 64)):
-        o = int(hd[i]["out_offset"]); lo, hi = int(hb.pcm_offsets[i]), int(hb.pcm_offsets[i + 1])
-        e2e_ok &= bool(np.array_equal(out_view[o:o + hi - lo], hb.pcm[lo:hi]))
-    e2e_value = n_samples * e2e_steps * world / e2e_s / 1e6
+    e2e = {}
+    if n_mine:
+        e2e_steps = args.e2e_steps or max(5, min(args.steps, 30))
+        hb, hd, hout_elems = job.host[0]
+        callers = max(1, args.e2e_callers)
+        # one context + pinned buffers per caller (a clx_ctx belongs to one host thread)
+        slots = []
+        for c in range(callers):
+            cx = cb.Context(device=local, n_streams=8, host_threads=max(1, host_threads // callers))
+            pb = cx.host_alloc(int(hb.data.size) + 64)
+            pb[: hb.data.size] = hb.data
+            slots.append((cx, pb, cx.host_alloc(4 * hout_elems + 64), np.zeros(hd.size, dtype=cb.RESULT_DTYPE)))
+
+        def run(mode, n_callers):
+            def worker(slot, n):
+                cx, pb, po, rs = slot
+                for _ in range(n):
+                    cx.decode_frames_raw(pb.ctypes.data, hb.data.size, hd.ctypes.data, hd.size, po.ctypes.data, hout_elems,
+                                         rs.ctypes.data, mode)
+            for slot in slots[:n_callers]:
+                worker(slot, 3)
+            barrier()
+            threads = [threading.Thread(target=worker, args=(slot, e2e_steps)) for slot in slots[:n_callers]]
+            t0 = time.perf_counter()
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            dt = time.perf_counter() - t0
+            barrier()
+            return max_over_ranks(dt), n_callers * e2e_steps
+
+        def check(mode):
+            ok = True
+            for cx, pb, po, rs in slots:
+                ok &= bool((rs["status"] == 0).all())
+                view = po[: 4 * hout_elems].view(np.int32) if mode == cb.OUT_PLANAR_I32 else po[: 2 * hout_elems].view(np.int16)
+                for i in range(0, hb.n_frames, max(1, hb.n_frames // 64)):
+                    o = int(hd[i]["out_offset"]); lo_, hi_ = int(hb.pcm_offsets[i]), int(hb.pcm_offsets[i + 1])
+                    exp = hb.pcm[lo_:hi_]
+                    if mode != cb.OUT_PLANAR_I32:
+                        exp = exp.reshape(int(hd[i]["n_channels"]), -1).T.reshape(-1).astype(np.int16)
+                    ok &= bool(np.array_equal(view[o:o + hi_ - lo_], exp))
+            return ok
+
+        for mode, key in ((cb.OUT_PLANAR_I32, "e2e"), (cb.OUT_INTERLEAVED_I16, "e2e_i16")):
+            if mode == cb.OUT_INTERLEAVED_I16 and cfg.bps > 16:
+                continue
+            dt1, n1 = run(mode, 1)
+            dt, n = run(mode, callers)
+            ok = check(mode)
+            d2h = (4 if mode == cb.OUT_PLANAR_I32 else 2) * hout_elems
+            e2e[key] = {"value": sum_over_ranks(hb.n_samples) * n / dt / 1e6, "unit": "Msamples/s", "steps": n, "callers": callers,
+                        "one_caller": sum_over_ranks(hb.n_samples) * n1 / dt1 / 1e6,
+                        "h2d_bytes_per_step": int(hb.data.size + hd.nbytes), "d2h_bytes_per_step": int(d2h + slots[0][3].nbytes),
+                        "bit_exact": ok, "output": "planar i32 (Block layout)" if mode == cb.OUT_PLANAR_I32
+                        else "interleaved little-endian i16 (a different metric row)"}
+            exact = exact and ok
 
     cpu = None
-    if rank == 0 and args.gpus == 1 and args.cpu_seconds > 0:
-        cores = os.cpu_count() or 1
-        v, reps, dt = cpu_decode_rate(hb, cores, args.cpu_seconds)
-        cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
-               "one_thread": cpu_single_thread_rate(hb),
-               "sample": f"{reps} x one full {args.workload} batch ({hb.n_samples} samples) in {dt:.1f}s, "
-                         f"frames sharded over {cores} threads (one_thread: the same port on a single thread, >= 1 s)"}
+    extra = None
+    if rank == 0 and world == 1:
+        if args.cpu_seconds > 0 and n_mine:
+            cores = os.cpu_count() or 1
+            hb = job.host[0][0]
+            v, reps, dt = cpu_decode_rate(hb, cores, args.cpu_seconds)
+            try:
+                one, _, _ = cpu_decode_rate(hb, 1, 1.0)
+            except Exception:
+                one = None
+            cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(), "one_thread": one,
+                   "sample": f"{reps} x one full {args.workload} unit ({hb.n_samples} samples) in {dt:.1f}s, frames sharded over "
+                             f"{cores} threads (one_thread: the same port on a single thread, >= 1 s)"}
+        if not args.no_extra and args.workload == "c2" and args.scaling == "weak":
+            job.close()
+            extra = {}
+            for wl, nu in (("c3", 8), ("c4", 48), ("c5", 4)):  # ~65 000 frames in flight like c2 (c5: memory-bound choice)
+                try:
+                    extra[wl] = short_line(cb, synth, ctx, wl, nu, min(args.streams, nu))
+                except Exception as e:  # never lose the headline line to an auxiliary measurement
+                    extra[wl] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
+        e2e_main = e2e.get("e2e", {"value": None, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / timed_steps, "repeats": repeats, "timed_steps": timed_steps,
-            "region_ms": region_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32 samples / int64 accumulate",
-            "data": "synthetic", "config": config, "bit_exact": exact and e2e_ok,
-            "clocks": clocks, "gpu_launches": int(gpu_launches),
-            "single_batch": {"kernel_ms": single_ms, "value": n_samples / (single_ms / 1e3) / 1e6,
+            "region_ms": regions, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "int32 samples / int64 accumulate", "data": "synthetic", "config": config, "bit_exact": bool(exact),
+            "clocks": clocks, "gpu_launches": gpu_launches,
+            "single_batch": {"kernel_ms": single_ms, "value": (job.unit_samples[0] / (single_ms / 1e3) / 1e6) if single_ms else None,
                              "unit": "Msamples/s", "note": "one batch, nothing else in flight (latency regime)"},
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(hb.data.size + hd.nbytes),
-                    "d2h_bytes_per_step": int(4 * hout_elems + results.nbytes)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": alg_bytes, "read_only_gbs": in_bytes * timed_steps / (ms / 1e3) / 1e9,
+            "e2e": e2e_main, "e2e_i16": e2e.get("e2e_i16"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "per": "GPU", "algorithmic_bytes_per_step": job.unit_alg[0] if n_mine else None,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "traffic_source": (traffic or {}).get("source")},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "workloads": extra,
         }
         print(json.dumps(line))
     if dist is not None:

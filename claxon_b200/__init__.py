@@ -20,8 +20,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, OPT_WARP_PER_FRAME, OPT_LANE_PER_FRAME,
-                   FRAME_VARIABLE_BLOCKING,
-                   FRAME_CRC16_VERIFIED)
+                   FRAME_VARIABLE_BLOCKING, FRAME_CRC16_VERIFIED,
+                   OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24)
 
 __all__ = ["Error", "Block", "FrameReader", "FlacReader", "StreamInfo", "Context", "DeviceBatch",
            "parse_frame_header", "demux_frames", "open_stream", "status_str", "DESC_DTYPE", "RESULT_DTYPE"]
@@ -166,7 +166,7 @@ class Context:
     """clx_ctx: one per host thread / GPU. Raises Error(NO_DEVICE) without a usable GPU."""
 
     def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False,
-                 warp_per_frame: bool = False, lane_per_frame: bool = False):
+                 warp_per_frame: bool = False, lane_per_frame: bool = False, host_threads: int = 0):
         """Default: device-resident batches and large calls use the lane-per-frame entropy kernel + lane-per-
         subframe prediction kernel (csrc/clx_seq.cu); small synchronous host-buffer calls (latency regime) use the
         warp-per-frame path (csrc/clx_coop.cu).  `warp_per_frame` / `lane_per_frame` force one of them everywhere,
@@ -174,7 +174,7 @@ class Context:
         self._L = _lib.load()
         flags = ((0 if verify_crc else OPT_NO_VERIFY_CRC) | (OPT_GENERIC_KERNEL_ONLY if generic_only else 0)
                  | (OPT_WARP_PER_FRAME if warp_per_frame else 0) | (OPT_LANE_PER_FRAME if lane_per_frame else 0))
-        opts = _lib.Options(device, flags, n_streams, 0)
+        opts = _lib.Options(device, flags, n_streams, host_threads)
         h = C.c_void_p()
         _check(self._L.clx_ctx_create(C.byref(opts), C.byref(h)))
         self._h = h
@@ -196,25 +196,29 @@ class Context:
         return int(self._L.clx_ctx_launch_count(self._h))
 
     def decode_frames(self, data, descs: np.ndarray, out: np.ndarray | None = None,
-                      out_elems: int | None = None):
-        """End-to-end host-buffer decode. Returns (out int32 ndarray, results ndarray)."""
+                      out_elems: int | None = None, mode: int = OUT_PLANAR_I32):
+        """End-to-end host-buffer decode. Returns (out ndarray, results ndarray).  `mode`: OUT_PLANAR_I32 (claxon's
+        Block layout, int32) or an interleaved little-endian form: OUT_INTERLEAVED_I32 (int32), _I16 (int16),
+        _I24 (uint8, 3 bytes per sample); out_offset / out_elems count samples in every mode."""
         buf = _as_u8(data)
         descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
+        if out_elems is None:
+            ends = descs["out_offset"] + descs["n_channels"].astype(np.uint64) * descs["block_size"]
+            out_elems = int(ends.max()) if descs.size else 0
         if out is None:
-            if out_elems is None:
-                ends = descs["out_offset"] + descs["n_channels"].astype(np.uint64) * descs["block_size"]
-                out_elems = int(ends.max()) if descs.size else 0
-            out = np.empty(max(1, out_elems), dtype=np.int32)
+            n = max(1, out_elems)
+            out = (np.empty(n, dtype=np.int16) if mode == OUT_INTERLEAVED_I16 else
+                   np.empty(3 * n, dtype=np.uint8) if mode == OUT_INTERLEAVED_I24 else np.empty(n, dtype=np.int32))
         results = np.zeros(descs.size, dtype=RESULT_DTYPE)
-        _check(self._L.clx_decode_frames(self._h, buf.ctypes.data, buf.size, descs.ctypes.data, descs.size,
-                                         out.ctypes.data, out.size, results.ctypes.data), self)
+        _check(self._L.clx_decode_frames_to(self._h, buf.ctypes.data, buf.size, descs.ctypes.data, descs.size,
+                                            out.ctypes.data, max(1, out_elems), results.ctypes.data, mode), self)
         return out, results
 
     def decode_frames_raw(self, bytes_ptr: int, nbytes: int, descs_ptr: int, n: int, out_ptr: int,
-                          out_elems: int, results_ptr: int):
+                          out_elems: int, results_ptr: int, mode: int = OUT_PLANAR_I32):
         """Same call on raw host addresses (pinned buffers owned by the caller)."""
-        _check(self._L.clx_decode_frames(self._h, bytes_ptr, nbytes, descs_ptr, n, out_ptr, out_elems,
-                                         results_ptr), self)
+        _check(self._L.clx_decode_frames_to(self._h, bytes_ptr, nbytes, descs_ptr, n, out_ptr, out_elems,
+                                            results_ptr, mode), self)
 
     def run_steps(self, batches: list["DeviceBatch"], steps: int, n_streams: int) -> float:
         """Decodes `steps` batches round-robin over `n_streams` streams; returns device ms (CUDA events)."""

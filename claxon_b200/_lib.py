@@ -36,7 +36,7 @@ class StreamInfoC(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("n_streams", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("host_threads", C.c_uint32)]
 
 
 assert C.sizeof(FrameDesc) == 40 and C.sizeof(FrameResult) == 8
@@ -45,6 +45,7 @@ OPT_NO_VERIFY_CRC = 1
 OPT_GENERIC_KERNEL_ONLY = 2
 OPT_WARP_PER_FRAME = 4
 OPT_LANE_PER_FRAME = 8
+OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24 = 0, 1, 2, 3
 FRAME_VARIABLE_BLOCKING = 1
 FRAME_CRC16_VERIFIED = 2
 
@@ -64,6 +65,7 @@ SYMBOLS = {
     "clx_ctx_destroy": (None, [_vp]),
     "clx_ctx_last_error": (C.c_char_p, [_vp]),
     "clx_decode_frames": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "clx_decode_frames_to": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _vp, _sz, _vp, C.c_uint32]),
     "clx_batch_create": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _sz, C.POINTER(_vp)]),
     "clx_batch_decode": (C.c_int, [_vp, _vp, C.c_uint32]),
     "clx_batch_sync": (C.c_int, [_vp, _vp]),

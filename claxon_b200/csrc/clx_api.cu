@@ -107,6 +107,7 @@ struct clx_ctx {
         clx_frame_result* d_results = nullptr; size_t results_cap = 0;
         int* d_need_hi = nullptr;
         uint8_t* d_params = nullptr; size_t params_cap = 0;  // fast path: per-subframe predictor parameters
+        uint8_t* d_conv = nullptr; size_t conv_cap = 0;      // interleaved output modes: converted samples
     };
     std::vector<Scratch> scratch;
     // pinned staging for the small per-frame tables: pageable memory would make the "async" copies
@@ -139,6 +140,7 @@ struct clx_batch {
     std::vector<uint8_t> crc_ok;
     std::vector<uint64_t> h_offset;
     std::vector<uint32_t> h_len;
+    std::vector<uint32_t> order;   // device position -> caller's frame index (empty: identity), see shape_order()
 };
 
 namespace {
@@ -222,6 +224,25 @@ bool valid_desc(const clx_frame_desc& d, size_t nbytes, size_t out_elems) {
            d.out_offset <= out_elems && elems <= out_elems - d.out_offset;
 }
 
+// The kernels map consecutive descriptors onto the lanes of a warp, and a warp advances at the pace of its longest
+// block: frames of one shape belong next to each other.  Fills `order` (position -> frame index) with the frames
+// [lo, hi) grouped by (channels, block size), stream order kept inside a group; returns false (order untouched) if
+// they are all of one shape already — the usual case: a file's frames differ only in its last block.
+bool shape_order(const clx_frame_desc* descs, size_t lo, size_t hi, std::vector<uint32_t>& order) {
+    bool mixed = false;
+    for (size_t i = lo + 1; i < hi && !mixed; i++)
+        mixed = descs[i].block_size != descs[lo].block_size || descs[i].n_channels != descs[lo].n_channels;
+    if (!mixed) return false;
+    order.resize(hi - lo);
+    for (size_t i = lo; i < hi; i++) order[i - lo] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const uint32_t ka = ((uint32_t)descs[a].n_channels << 16) | descs[a].block_size;
+        const uint32_t kb = ((uint32_t)descs[b].n_channels << 16) | descs[b].block_size;
+        return ka > kb;
+    });
+    return true;
+}
+
 // Chooses how a set of frames maps onto the cooperative kernel (frames per CTA, shared memory).
 // Two fast paths, two regimes.  The lane-per-frame path (clx_seq.cu) has the fewest instructions per
 // sample and is what a stream of batches should use; but a lane walks its whole frame alone, so one call
@@ -240,8 +261,16 @@ clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t 
         max_bs = std::max<uint32_t>(max_bs, descs[i].block_size);
         max_bps = std::max<uint32_t>(max_bps, descs[i].bits_per_sample);
     }
+    // The lane-per-frame index pass walks (channels - 1) * block_size Rice codes of a frame with ONE lane: fine for
+    // stereo blocks of a few thousand samples, hopeless for 8 x 16384 (BASELINE.json's stress shape: a 7 ms serial
+    // walk however few frames there are).  Such frames go to the warp-per-frame path, which parallelises the bit
+    // scan inside the frame.
+    uint64_t serial_codes = 0;
+    for (size_t i = 0; i < n; i++)
+        serial_codes = std::max<uint64_t>(serial_codes, (uint64_t)(descs[i].n_channels - 1) * descs[i].block_size);
+    const bool long_walk = serial_codes > 24576 && !ctx->lane_per_frame_always;
     if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame &&
-        !(latency_call && !ctx->lane_per_frame_always)) {
+        !long_walk && !(latency_call && !ctx->lane_per_frame_always)) {
         plan.G = 2;
         plan.narrow = max_bps <= 16 ? 1u : 0u;
         plan.max_bs = max_bs;
@@ -281,6 +310,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
     if (opts && (opts->flags & CLX_OPT_WARP_PER_FRAME)) ctx->warp_per_frame = true;
     if (opts && (opts->flags & CLX_OPT_LANE_PER_FRAME)) ctx->lane_per_frame_always = true;
     ctx->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (opts && opts->host_threads) ctx->host_threads = std::max(1u, std::min(64u, opts->host_threads));
     *out = ctx;
     return CLX_OK;
 }
@@ -291,6 +321,7 @@ void clx_ctx_destroy(clx_ctx* ctx) {
     for (auto& s : ctx->scratch) {
         cudaFree(s.d_bytes); cudaFree(s.d_descs); cudaFree(s.d_out); cudaFree(s.d_results); cudaFree(s.d_need_hi);
         cudaFree(s.d_params);
+        cudaFree(s.d_conv);
     }
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
@@ -308,8 +339,19 @@ void* clx_ctx_stream(clx_ctx* ctx, uint32_t i) { return ctx ? (void*)ctx->stream
 // ---------------------------------------------------------------------------------
 int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
                       size_t n_frames, int32_t* out, size_t out_elems, clx_frame_result* results) {
-    if (!ctx || (!bytes && nbytes) || (!descs && n_frames) || (!results && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
+    return clx_decode_frames_to(ctx, bytes, nbytes, descs, n_frames, out, out_elems, results, CLX_OUT_PLANAR_I32);
+}
+
+int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                         size_t n_frames, void* out_v, size_t out_elems, clx_frame_result* results, uint32_t mode) {
+    if (!ctx || (!bytes && nbytes) || (!descs && n_frames) || (!results && n_frames) || mode > CLX_OUT_INTERLEAVED_I24)
+        return CLX_ERR_INVALID_ARGUMENT;
     if (n_frames == 0) return CLX_OK;
+    uint8_t* const out = static_cast<uint8_t*>(out_v);
+    const size_t esize = clx::output_elem_size(mode);
+    const uint32_t max_bps = mode == CLX_OUT_INTERLEAVED_I16 ? 16u : mode == CLX_OUT_INTERLEAVED_I24 ? 24u : 32u;
+    for (size_t i = 0; i < n_frames; i++)
+        if (descs[i].bits_per_sample > max_bps) return CLX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!out) return CLX_ERR_INVALID_ARGUMENT;
     for (size_t i = 0; i < n_frames; i++)
@@ -335,6 +377,7 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
     memcpy(ctx->h_descs, descs, n_frames * sizeof(clx_frame_desc));
     struct Span { size_t f0, f1; uint64_t b0, b1, o0, o1; };
     std::vector<Span> spans;
+    std::vector<uint32_t> device_order;  // empty: the device sees the frames in the caller's order
     for (size_t c = 0; c < n_chunks; c++) {
         Span s{n_frames * c / n_chunks, n_frames * (c + 1) / n_chunks, ~0ull, 0, ~0ull, 0};
         for (size_t i = s.f0; i < s.f1; i++) {
@@ -347,6 +390,18 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         // The device copy of the chunk's output keeps the host layout's alignment (offset mod 4 elements, so
         // 16-byte stores stay possible) but the copy back covers exactly [o0, o1): it never touches an element
         // before the chunk's first frame, so neighbouring chunks cannot overlap on the host side.
+        // device order of the chunk's frames: grouped by shape (position p of the chunk holds frame order[p])
+        std::vector<uint32_t> order;
+        if (shape_order(descs, s.f0, s.f1, order)) {
+            if (device_order.empty()) {
+                device_order.resize(n_frames);
+                for (size_t i = 0; i < n_frames; i++) device_order[i] = (uint32_t)i;
+            }
+            for (size_t p = 0; p < order.size(); p++) {
+                device_order[s.f0 + p] = order[p];
+                ctx->h_descs[s.f0 + p] = descs[order[p]];
+            }
+        }
         for (size_t i = s.f0; i < s.f1; i++) {
             ctx->h_descs[i].byte_offset -= s.b0;
             ctx->h_descs[i].out_offset -= s.o0 & ~3ull;
@@ -378,12 +433,21 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
         if (!sc.d_need_hi) CUD(cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
         const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf, n_frames <= kLatencyRegimeFrames);
         if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return drain(rc);
+        if (mode != CLX_OUT_PLANAR_I32 && (rc = grow(ctx, sc.d_conv, sc.conv_cap, (lead + no + 4) * esize, 4096))) return drain(rc);
         enqueued = c + 1;
         CUD(cudaMemcpyAsync(sc.d_bytes, bytes + s.b0, nb, cudaMemcpyHostToDevice, st));
         CUD(cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc), cudaMemcpyHostToDevice, st));
         CUD(clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results, sc.d_need_hi,
                                sc.d_params, plan, st, &ctx->launches));
-        CUD(cudaMemcpyAsync(out + s.o0, sc.d_out + lead, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (mode == CLX_OUT_PLANAR_I32) {
+            CUD(cudaMemcpyAsync(out + s.o0 * esize, sc.d_out + lead, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        } else {
+            uint32_t max_elems = 0;
+            for (size_t i = s.f0; i < s.f1; i++) max_elems = std::max<uint32_t>(max_elems, (uint32_t)descs[i].n_channels * descs[i].block_size);
+            CUD(clx::launch_interleave(sc.d_descs, (uint32_t)nf, max_elems, sc.d_out, sc.d_conv, mode, st));
+            ctx->launches++;
+            CUD(cudaMemcpyAsync(out + s.o0 * esize, sc.d_conv + lead * esize, no * esize, cudaMemcpyDeviceToHost, st));
+        }
         CUD(cudaMemcpyAsync(ctx->h_results + s.f0, sc.d_results, nf * sizeof(clx_frame_result), cudaMemcpyDeviceToHost, st));
     }
 #ifdef CLX_EXPERIMENT
@@ -398,7 +462,9 @@ int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const c
     for (size_t c = 0; c < n_chunks; c++) CUD(cudaStreamSynchronize(ctx->streams[c]));
 #undef CUD
     const double t3 = trace ? now() : 0;
-    memcpy(results, ctx->h_results, n_frames * sizeof(clx_frame_result));
+    if (device_order.empty()) memcpy(results, ctx->h_results, n_frames * sizeof(clx_frame_result));
+    else
+        for (size_t p = 0; p < n_frames; p++) results[device_order[p]] = ctx->h_results[p];
     apply_crc(ctx, bytes, descs, results, n_frames);
     if (trace)
         fprintf(stderr, "[clx] frames=%zu chunks=%zu submit=%.3f ms crc=%.3f ms wait=%.3f ms apply=%.3f ms\n", n_frames,
@@ -430,7 +496,13 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_params, clx::coop_params_bytes(b->plan, b->n_frames) + 16);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(b->d_descs, descs, n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (shape_order(descs, 0, n_frames, b->order)) {
+            std::vector<clx_frame_desc> sorted(n_frames);
+            for (size_t p = 0; p < n_frames; p++) sorted[p] = descs[b->order[p]];
+            e = cudaMemcpy(b->d_descs, sorted.data(), n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
+        } else e = cudaMemcpy(b->d_descs, descs, n_frames * sizeof(clx_frame_desc), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_stop);
     if (e != cudaSuccess) {
@@ -526,7 +598,13 @@ int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, c
     if (rc) return rc;
     if (out) CU(ctx, cudaMemcpy(out, b->d_out, std::min(out_elems, b->out_elems) * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (results) {
-        CU(ctx, cudaMemcpy(results, b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+        if (b->order.empty()) {
+            CU(ctx, cudaMemcpy(results, b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<clx_frame_result> dev(b->n_frames);
+            CU(ctx, cudaMemcpy(dev.data(), b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
+            for (size_t p = 0; p < b->n_frames; p++) results[b->order[p]] = dev[p];
+        }
         if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {
             std::vector<uint8_t> tmp;
             for (size_t i = 0; i < b->n_frames; i++) {

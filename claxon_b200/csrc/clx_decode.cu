@@ -702,7 +702,7 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
         if (e != cudaSuccess) return e;
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, d_generic, CLX_INTERNAL_NEED_GENERIC);
-        if (launches) *launches += plan.G == 2 ? 5 : 2;  // entropy + prediction (one instance per order class)
+        if (launches) *launches += plan.G == 2 ? 3 : 2;  // index pass + two decode instances / entropy + prediction
     } else {
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, nullptr, 0);

@@ -74,13 +74,15 @@ struct DeviceIO {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads (C2: 0.36
-    // on average), so one predicated copy per group keeps the ring ahead; a lane whose ring has fallen
-    // behind (a run of maximal codes) is sent to the slow path, whose ensure() refills it.  The group
-    // needs quads up to (bitpos >> 7) + 3; copies of the last WAITN groups may still be in flight.
+    // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads (C2: 0.36 on
+    // average): one predicated copy per group keeps the ring ahead of light streams, a second one — behind a
+    // branch that light streams never take — keeps it ahead of dense ones (large Rice parameters: a quad per
+    // group and more).  The group needs quads up to (bitpos >> 7) + 3; copies of the last WAITN groups may
+    // still be in flight.  False: the ring is not far enough ahead (the caller refills it with ensure()).
     __device__ __forceinline__ bool prefetch_group(uint32_t bitpos) {
         const uint32_t q0 = bitpos >> 7;
         if (fq < q0 + RQ) { issue(fq); fq++; }
+        while (fq < q0 + RQ) { issue(fq); fq++; }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group %0;" ::"n"(WAITN) : "memory");
         return fq >= q0 + 4 + WAITN;
@@ -451,10 +453,11 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
     if (max_bs & 31) seq_flush<true>(tile_ptr(fill_s), pr, max_bs & ~31u, lane, any_wasted);
 }
 
-// One instance per order class (CLASS 0: max order of the warp <= 4, 1: <= 8, 2: <= 12, 3: <= 32), launched
-// back to back: a warp does its work in the instance of its class and leaves the others at once, so the
-// 8-tap instance is not charged the registers of the 32-tap one.
-template <int CLASS>
+// Two instances, launched back to back: GROUP 0 takes the warps whose largest predictor order is at most 12 (with
+// an 8-tap and a 12-tap body: every warp of a batch of mixed orders runs at once), GROUP 1 the warps with orders
+// up to 32 (non-subset streams), whose body needs half as many registers again.  A warp does its work in the
+// instance of its group and leaves the other at once.
+template <int GROUP>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
                         uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
@@ -506,8 +509,8 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     }
     if (!__any_sync(0xffffffffu, active)) return;
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
-    const int cls = max_order <= 4 ? 0 : max_order <= 8 ? 1 : max_order <= 12 ? 2 : 3;
-    if (cls != CLASS) return;
+    const int cls = max_order <= 8 ? 0 : max_order <= 12 ? 1 : 2;
+    if ((cls == 2) != (GROUP == 1)) return;
     if (active) {
         L.rc.io.open(ring, lane, bytes, buf_bytes, descs[f].byte_offset);
         L.init(*sp, bs, bit0 + byte_len * 8);
@@ -537,17 +540,19 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t outp_s = (uint32_t)__cvta_generic_to_shared(&s_outp[warp][0]);
 #define CLX_ROWS(T, UU, A, F) decode_rows<T, UU, A, F>(L, bs, order, shift, sp, active, tile, tile_s, pr, outp_s, s_slow[warp][lane], lane, all_vec, any_wasted, smin, smax)
-    constexpr int T = CLASS == 0 ? 4 : CLASS == 1 ? 8 : CLASS == 2 ? 12 : 32;
-    constexpr int UU = CLASS <= 1 ? 8 : 4;
-    if (all_narrow) {
-        if (fmode == 2) CLX_ROWS(T, UU, int, 2);
-        else if (fmode == 1) CLX_ROWS(T, UU, int, 1);
-        else CLX_ROWS(T, UU, int, 0);
-    } else {
-        if (fmode == 2) CLX_ROWS(T, UU, long long, 2);
-        else if (fmode == 1) CLX_ROWS(T, UU, long long, 1);
-        else CLX_ROWS(T, UU, long long, 0);
-    }
+    // straight-line flush variants only where they pay: the i32-accumulator bodies (16-bit audio)
+#define CLX_BODY(T, UU)                                    \
+    do {                                                   \
+        if (all_narrow) {                                  \
+            if (fmode == 2) CLX_ROWS(T, UU, int, 2);       \
+            else if (fmode == 1) CLX_ROWS(T, UU, int, 1);  \
+            else CLX_ROWS(T, UU, int, 0);                  \
+        } else CLX_ROWS(T, UU, long long, 0);              \
+    } while (0)
+    if (GROUP == 1) CLX_BODY(32, 4);
+    else if (cls == 0) CLX_BODY(8, 8);
+    else CLX_BODY(12, 4);
+#undef CLX_BODY
 #undef CLX_ROWS
     if (!active) return;
     // The subframe must end inside the frame; the lane of the last subframe locates the CRC-16 footer
@@ -609,7 +614,7 @@ cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fra
         const size_t dyn = 0;
 #endif
 #define CLX_DEC(C) decode_subframes_kernel<C><<<g2, b2, dyn, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic)
-        CLX_DEC(0); CLX_DEC(1); CLX_DEC(2); CLX_DEC(3);
+        CLX_DEC(0); CLX_DEC(1);
 #undef CLX_DEC
     }
     return cudaGetLastError();

@@ -40,6 +40,10 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
                           void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
+// clx_output.cu: planar i32 -> interleaved little-endian samples (CLX_OUT_* modes), frame by frame
+uint32_t output_elem_size(uint32_t mode);
+cudaError_t launch_interleave(const clx_frame_desc* d_descs, uint32_t n_frames, uint32_t max_frame_elems, const int32_t* d_planar,
+                              void* d_dst, uint32_t mode, cudaStream_t stream);
 #ifdef CLX_EXPERIMENT
 extern int g_exp_which;  // measurement builds only: bit 0 = index pass, bit 1 = decode pass
 extern int g_exp_dyn_smem;

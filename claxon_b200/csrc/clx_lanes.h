@@ -111,7 +111,7 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 // IO policy (DeviceIO in clx_fused.cu, HostIO in tools/seq_host.cpp):
 //   uint32_t word(uint32_t wi)            big-endian word `wi` of the frame (relative to its 16-byte aligned base)
 //   void ensure(uint32_t bitpos)          the bits from bitpos on (ring size minus slack) are readable through word()
-//   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: take the slow path
+//   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: ensure() before reading on
 //   void seek_next(uint32_t wi), uint32_t next_raw()   sequential word reads, bytes as stored (the register window's refill)
 
 // ---------------------------------------------------------------------------------
@@ -255,7 +255,7 @@ struct RiceCursor {
     // only because its codes are too long TOGETHER is retried one form down first.)
     template <bool VALUES>
     CLX_HD bool fast_group_t(int32_t (&e)[8]) {
-        if (!io.prefetch_group(o)) { n_fast = 0; return false; }
+        if (!io.prefetch_group(o)) io.ensure(o);  // the ring had fallen behind (a dense stretch): refill it, blocking
         const uint32_t o0 = o, w0 = W0, w1 = W1, w2 = W2;
         bool bad = codes8_by_cap<VALUES>(e);
         if (bad && ncap > 1) {  // once more, one code per refill: needs the window back

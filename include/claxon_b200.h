@@ -78,7 +78,8 @@ typedef struct clx_options {
     int32_t device;        /* CUDA device ordinal */
     uint32_t flags;        /* CLX_OPT_* */
     uint32_t n_streams;    /* internal CUDA streams for host<->device pipelining (0 = default 2) */
-    uint32_t reserved;
+    uint32_t host_threads; /* host threads for the CRC-16 pass (0 = default: min(32, hardware threads));
+                              give each rank its share when several ranks run on one host */
 } clx_options;
 #define CLX_OPT_NO_VERIFY_CRC 1u /* mimic claxon's cfg(fuzzing): skip CRC-8/CRC-16 checks */
 #define CLX_OPT_GENERIC_KERNEL_ONLY 2u /* testing: bypass the fast path */
@@ -137,6 +138,23 @@ const char* clx_ctx_last_error(const clx_ctx* ctx); /* CUDA error text for CLX_E
  * aborts the batch; its output region is fully overwritten (never stale). */
 int clx_decode_frames(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
                       size_t n_frames, int32_t* out, size_t out_elems, clx_frame_result* results);
+
+/* Output stage: the same call with the samples delivered INTERLEAVED — for each
+ * inter-channel sample every channel in turn, the order FlacSamples yields them in (src/lib.rs:473-519)
+ * — as little-endian integers of 2, 3 or 4 bytes: what a WAV writer stores (examples/decode.rs:48-62)
+ * and what the STREAMINFO MD5 is defined over (src/metadata.rs:52-53).  The conversion runs on the
+ * device, so 16-bit audio crosses PCIe as 2 bytes per sample.  `out_elems` and descs[i].out_offset
+ * count SAMPLES (elements of 2 / 3 / 4 bytes); a frame occupies n_channels * block_size of them as in
+ * the planar layout.  CLX_OUT_INTERLEAVED_I16 / _I24 require every frame's bits_per_sample to be at
+ * most 16 / 24 (else CLX_ERR_INVALID_ARGUMENT); a sample that nevertheless does not fit (only an invalid
+ * stream has them) is truncated to the element size like `sample as i16` in examples/decode.rs:52.
+ * CLX_OUT_PLANAR_I32 is clx_decode_frames. */
+#define CLX_OUT_PLANAR_I32 0u
+#define CLX_OUT_INTERLEAVED_I32 1u
+#define CLX_OUT_INTERLEAVED_I16 2u
+#define CLX_OUT_INTERLEAVED_I24 3u
+int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                         size_t n_frames, void* out, size_t out_elems, clx_frame_result* results, uint32_t mode);
 
 /* Device-resident variant: upload once, decode many times (kernel-only timing), read back. */
 int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,

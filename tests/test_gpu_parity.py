@@ -335,3 +335,149 @@ def test_c3_and_c5_large_by_checksum(ctx):
         out, res = ctx.decode_frames(b.data, descs, out_elems=out_elems)
         assert (res["status"] == 0).all()
         assert hashlib.sha1(out[:b.n_samples].tobytes()).digest() == hashlib.sha1(b.pcm.tobytes()).digest()
+
+
+# --------------------------------------------------------------------------- output stage (interleave + narrow)
+
+def _interleaved_expected(b, descs, out_elems, mode):
+    """Oracle PCM (planar) re-laid out on the host the way FlacSamples yields it (src/lib.rs:473-519)."""
+    bad, st, ref = O.decode_batch(b.data, b.frame_offsets[:-1], b.frame_lengths, descs["out_offset"], out_elems, n_threads=8)
+    assert bad == 0
+    exp = np.zeros(out_elems, dtype=np.int32)
+    for i in range(b.n_frames):
+        o, nch, bs = int(descs[i]["out_offset"]), int(descs[i]["n_channels"]), int(descs[i]["block_size"])
+        exp[o:o + nch * bs] = ref[o:o + nch * bs].reshape(nch, bs).T.reshape(-1)
+    return exp
+
+
+@pytest.mark.parametrize("case", ["c2-ms", "c4-files", "ragged-3ch-24bit", "tiny-blocks-8bit", "8ch-12bit-fixed", "mono-20bit-k0"])
+def test_interleaved_output_modes_vs_oracle(ctx, case):
+    """the device-side interleave + narrow stage against the oracle's PCM, every element size."""
+    b = synth.generate(SYNTH_CASES[case])
+    descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
+    bps = int(descs["bits_per_sample"].max())
+    exp = _interleaved_expected(b, descs, out_elems, None)
+    live = np.zeros(out_elems, dtype=bool)
+    for d in descs:
+        live[int(d["out_offset"]):int(d["out_offset"]) + int(d["n_channels"]) * int(d["block_size"])] = True
+    out32, res = ctx.decode_frames(b.data, descs, out_elems=out_elems, mode=cb.OUT_INTERLEAVED_I32)
+    assert (res["status"] == 0).all() and np.array_equal(out32[:out_elems][live], exp[live])
+    if bps <= 24:
+        out24, res = ctx.decode_frames(b.data, descs, out_elems=out_elems, mode=cb.OUT_INTERLEAVED_I24)
+        got = out24[:3 * out_elems].reshape(-1, 3).astype(np.int32)
+        val = got[:, 0] | (got[:, 1] << 8) | (got[:, 2] << 16)
+        val = (val ^ 0x800000) - 0x800000  # sign-extend 24 bits
+        assert (res["status"] == 0).all() and np.array_equal(val[live], exp[live])
+    if bps <= 16:
+        out16, res = ctx.decode_frames(b.data, descs, out_elems=out_elems, mode=cb.OUT_INTERLEAVED_I16)
+        assert out16.dtype == np.int16 and (res["status"] == 0).all()
+        # (the c4 generator's forced Rice parameters push some "16-bit" samples out of range: truncated like `as i16`)
+        assert np.array_equal(out16[:out_elems][live], exp[live].astype(np.int16))
+    else:
+        with pytest.raises(cb.Error) as e:  # 20/24-bit samples do not fit 16 bits: refused, not truncated
+            ctx.decode_frames(b.data, descs, out_elems=out_elems, mode=cb.OUT_INTERLEAVED_I16)
+        assert e.value.status == 90
+
+
+def test_interleaved_output_md5_of_reference_fixtures(ctx, golden):
+    """The STREAMINFO MD5 (libFLAC's encoder-side digest, src/metadata.rs:52-53) is defined over exactly what the
+    interleaved little-endian modes deliver: hash the device's bytes as they come."""
+    for name in ("pop", "short", "wasted_bits"):
+        data = golden[f"{name}__bytes"]
+        si, first = cb.open_stream(data)
+        descs, nxt, total, stop = cb.demux_frames(data, first)
+        assert stop == 1 and si.bits_per_sample == 16
+        out, res = ctx.decode_frames(data, descs, out_elems=total, mode=cb.OUT_INTERLEAVED_I16)
+        assert (res["status"] == 0).all()
+        md5 = hashlib.md5()
+        for d in descs:
+            o, n = int(d["out_offset"]), int(d["n_channels"]) * int(d["block_size"])
+            md5.update(out[o:o + n].astype("<i2").tobytes())
+        assert md5.digest() == si.md5sum, name
+    # a synthetic stereo file carries the digest of its by-construction PCM
+    b = synth.workload("c4", 22)
+    file_bytes = np.frombuffer(synth.make_file(b, 0, 22), dtype=np.uint8)
+    si, first = cb.open_stream(file_bytes)
+    descs, nxt, total, stop = cb.demux_frames(file_bytes, first)
+    out, res = ctx.decode_frames(file_bytes, descs, out_elems=total, mode=cb.OUT_INTERLEAVED_I16)
+    md5 = hashlib.md5()
+    for d in descs:
+        o, n = int(d["out_offset"]), int(d["n_channels"]) * int(d["block_size"])
+        md5.update(out[o:o + n].astype("<i2").tobytes())
+    assert (res["status"] == 0).all() and md5.digest() == si.md5sum
+
+
+# --------------------------------------------------------------------------- BASELINE.json's configurations at full size
+
+@pytest.mark.parametrize("name,frames", [("c3", 8192), ("c4", 11000), ("c5", 512)])
+def test_full_size_configs_vs_oracle(name, frames):
+    """configs[2..4] at (per-GPU) full size through the device-resident throughput path, against the ORACLE's PCM
+    (and the generator's by-construction PCM): c3 = the whole 8192-frame batch; c4 = 1000 files with forced Rice
+    parameters 0..14 (the largest of them code 16-bit audio with residuals beyond 16 bits); c5 = one GPU's eighth
+    of the 4096-frame stress batch (8 channels, LPC order 32, block size 16384)."""
+    c = cb.Context(device=0, lane_per_frame=True)
+    b = synth.workload(name, frames)
+    descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
+    assert out_elems == b.n_samples
+    bad, st, ref = O.decode_batch(b.data, b.frame_offsets[:-1], b.frame_lengths, descs["out_offset"], out_elems,
+                                  n_threads=min(64, os.cpu_count() or 8))
+    assert bad == 0 and hashlib.sha1(ref.tobytes()).digest() == hashlib.sha1(b.pcm.tobytes()).digest()
+    dev = c.upload(b.data, descs, out_elems)
+    dev.decode(0)
+    out, res = dev.read()
+    dev.close()
+    c.close()
+    assert (res["status"] == 0).all() and np.array_equal(res["consumed"], b.frame_lengths)
+    if not np.array_equal(out[:out_elems], ref):
+        badf = [i for i in range(b.n_frames) if not np.array_equal(
+            out[int(descs[i]["out_offset"]):int(descs[i]["out_offset"]) + int(descs[i]["n_channels"]) * int(descs[i]["block_size"])],
+            ref[int(descs[i]["out_offset"]):int(descs[i]["out_offset"]) + int(descs[i]["n_channels"]) * int(descs[i]["block_size"])])]
+        raise AssertionError(f"{name}: {len(badf)} frames differ from the oracle, first {badf[:5]}")
+
+
+def test_resident_batch_reports_crc_mismatch():
+    """The device-resident path verifies the frame CRC-16 too (src/frame.rs:752-763): a flipped residual bit comes
+    back as "frame CRC mismatch", not as CLX_OK with wrong PCM."""
+    c = cb.Context(device=0)
+    b = synth.workload("c2", 64)
+    data = b.data.copy()
+    victims = [3, 40]
+    for v in victims:
+        data[int(b.frame_offsets[v]) + int(b.frame_lengths[v]) // 2] ^= 0x10
+    descs, out_elems = cb.descs_from_offsets(data, b.frame_offsets[:-1], b.frame_lengths)
+    dev = c.upload(data, descs, out_elems)
+    dev.decode(0)
+    out, res = dev.read()
+    bad, st, ref = O.decode_batch(data, b.frame_offsets[:-1], b.frame_lengths, descs["out_offset"], out_elems, n_threads=4)
+    assert np.array_equal(res["status"], st) and set(np.nonzero(st)[0].tolist()) == set(victims)
+    dev.close()
+    c.close()
+
+
+def test_constant_frames_through_read_batch(ctx):
+    """Digital silence: 14-byte frames that decode to 8192 samples each (the batched reader used to size
+    its buffer from the remaining BYTES and failed on such streams)."""
+    cfg = synth.SynthConfig(n_frames=40, block_size=4096, n_channels=2, bps=16, stereo_mode=0, type_mask=1)
+    b = synth.generate(cfg)
+    assert b.data.size < 40 * 64
+    fr = cb.FrameReader(b.data, ctx)
+    blocks = fr.read_batch(1000)
+    assert len(blocks) == 40
+    for i, blk in enumerate(blocks):
+        lo, hi = int(b.pcm_offsets[i]), int(b.pcm_offsets[i + 1])
+        assert np.array_equal(blk.into_buffer(), b.pcm[lo:hi])
+    assert fr.read_batch(10) == []
+
+
+def test_tightly_packed_odd_blocks_many_chunks(ctx):
+    """>= 256 frames (several chunks on several streams) whose out_offsets are NOT multiples of 4 and
+    leave no gap: neighbouring chunks must not touch each other's samples."""
+    cfg = synth.SynthConfig(n_frames=700, block_size=333, n_channels=1, bps=16, type_mask=12, lpc_min_order=1,
+                            lpc_max_order=8, rice_mode=-1, max_porder=0)
+    b = synth.generate(cfg)
+    descs, _ = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
+    descs["out_offset"] = np.arange(b.n_frames, dtype=np.uint64) * 333 + 1  # packed, odd
+    out = np.full(b.n_frames * 333 + 2, 77, dtype=np.int32)
+    out, res = ctx.decode_frames(b.data, descs, out=out)
+    assert (res["status"] == 0).all() and out[0] == 77 and out[-1] == 77
+    assert np.array_equal(out[1:-1], b.pcm)
