@@ -167,10 +167,10 @@ int grow(clx_ctx* ctx, T*& ptr, size_t& cap, size_t need, size_t slack) {
     return CLX_OK;
 }
 
-// The frame CRC-16 (src/frame.rs:752-763) is checked on the host, and takes effect only when the
-// subframes decoded, so subframe errors keep their precedence over "frame CRC mismatch".  The CRC of
-// the span the descriptor claims (byte_len) is computed while the GPU is busy; after the kernels a
-// frame only needs a second look if it ended somewhere else.
+// Host-side frame CRC-16 (src/frame.rs:752-763) for device-resident batches: their bytes never change, so the
+// checksum of every claimed span is taken once, when the batch is created (the host-buffer call checks on the
+// device instead, clx_crc.cu).  It takes effect only when the subframes decoded, so subframe errors keep their
+// precedence over "frame CRC mismatch"; a frame that ended somewhere else than claimed gets a second look.
 void precompute_crc_range(const uint8_t* bytes, const clx_frame_desc* descs, uint8_t* verdict, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; i++) {
         const clx_frame_desc& d = descs[i];
@@ -192,23 +192,6 @@ void precompute_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* de
     ctx->pool->run(nt, [&](unsigned part, unsigned parts) {
         precompute_crc_range(bytes, descs, verdict, n * part / parts, n * (part + 1) / parts);
     });
-}
-
-void apply_crc(clx_ctx* ctx, const uint8_t* bytes, const clx_frame_desc* descs, clx_frame_result* results, size_t n) {
-    if (ctx->flags & CLX_OPT_NO_VERIFY_CRC) return;
-    for (size_t i = 0; i < n; i++) {
-        if (results[i].status != CLX_OK) continue;
-        const clx_frame_desc& d = descs[i];
-        const uint32_t consumed = results[i].consumed;
-        bool ok;
-        if (consumed == d.byte_len) ok = ctx->crc_verdict[i] != 0;
-        else {  // the frame ended before the end of the span it was given (boundary was a guess)
-            const uint8_t* f = bytes + d.byte_offset;
-            const uint16_t stored = (uint16_t)(((uint32_t)f[consumed - 2] << 8) | f[consumed - 1]);
-            ok = clx_crc16(f, consumed - 2) == stored;
-        }
-        if (!ok) results[i].status = CLX_ERR_FRAME_CRC_MISMATCH;
-    }
 }
 
 void build_graph(clx_ctx* ctx, clx_batch* b);
@@ -430,7 +413,7 @@ int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, cons
         if ((rc = grow(ctx, sc.d_descs, sc.descs_cap, nf, 64))) return drain(rc);
         if ((rc = grow(ctx, sc.d_out, sc.out_cap, lead + no + 4, 4096))) return drain(rc);
         if ((rc = grow(ctx, sc.d_results, sc.results_cap, nf, 64))) return drain(rc);
-        if (!sc.d_need_hi) CUD(cudaMalloc((void**)&sc.d_need_hi, 2 * sizeof(int)));
+        if (!sc.d_need_hi) CUD(cudaMalloc((void**)&sc.d_need_hi, 4 * sizeof(int)));
         const clx::CoopPlan plan = make_plan(ctx, descs + s.f0, nf, n_frames <= kLatencyRegimeFrames);
         if ((rc = grow(ctx, sc.d_params, sc.params_cap, clx::coop_params_bytes(plan, (uint32_t)nf) + 16, 4096))) return drain(rc);
         if (mode != CLX_OUT_PLANAR_I32 && (rc = grow(ctx, sc.d_conv, sc.conv_cap, (lead + no + 4) * esize, 4096))) return drain(rc);
@@ -439,6 +422,10 @@ int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, cons
         CUD(cudaMemcpyAsync(sc.d_descs, ctx->h_descs + s.f0, nf * sizeof(clx_frame_desc), cudaMemcpyHostToDevice, st));
         CUD(clx::launch_decode(sc.d_bytes, nb_pad, sc.d_descs, (uint32_t)nf, sc.d_out, sc.d_results, sc.d_need_hi,
                                sc.d_params, plan, st, &ctx->launches));
+        if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {  // src/frame.rs:752-763, after the subframes, on the device
+            CUD(clx::launch_crc16(sc.d_bytes, sc.d_descs, (uint32_t)nf, sc.d_results, st));
+            ctx->launches++;
+        }
         if (mode == CLX_OUT_PLANAR_I32) {
             CUD(cudaMemcpyAsync(out + s.o0 * esize, sc.d_out + lead, no * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         } else {
@@ -457,18 +444,15 @@ int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, cons
 #endif
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t1 = trace ? now() : 0;
-    precompute_crc(ctx, bytes, descs, n_frames);  // host work, overlapped with the copies and kernels above
-    const double t2 = trace ? now() : 0;
     for (size_t c = 0; c < n_chunks; c++) CUD(cudaStreamSynchronize(ctx->streams[c]));
 #undef CUD
-    const double t3 = trace ? now() : 0;
+    const double t2 = trace ? now() : 0;
     if (device_order.empty()) memcpy(results, ctx->h_results, n_frames * sizeof(clx_frame_result));
     else
         for (size_t p = 0; p < n_frames; p++) results[device_order[p]] = ctx->h_results[p];
-    apply_crc(ctx, bytes, descs, results, n_frames);
     if (trace)
-        fprintf(stderr, "[clx] frames=%zu chunks=%zu submit=%.3f ms crc=%.3f ms wait=%.3f ms apply=%.3f ms\n", n_frames,
-                n_chunks, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+        fprintf(stderr, "[clx] frames=%zu chunks=%zu submit=%.3f ms wait=%.3f ms results=%.3f ms\n", n_frames, n_chunks, t1 - t0,
+                t2 - t1, now() - t2);
     return CLX_OK;
 }
 
@@ -493,7 +477,7 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_descs, std::max<size_t>(1, n_frames) * sizeof(clx_frame_desc));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_out, (out_elems + 4) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_params, clx::coop_params_bytes(b->plan, b->n_frames) + 16);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {

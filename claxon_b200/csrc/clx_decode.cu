@@ -695,14 +695,14 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
     dim3 grid((n_frames + per_cta - 1) / per_cta), block(per_cta);
     int* d_generic = d_flags;      // set by the cooperative kernel: some frames need the generic kernel
     int* d_need_hi = d_flags + 1;  // set by the 12-tap generic instance: some frames need 32 taps
-    cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream);  // [0] generic, [1] 32 taps, [2] i64 retry
     if (e != cudaSuccess) return e;
     if (plan.G > 0 && d_params != nullptr) {
         e = launch_coop(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, d_generic, d_params, plan, stream);
         if (e != cudaSuccess) return e;
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, d_generic, CLX_INTERNAL_NEED_GENERIC);
-        if (launches) *launches += plan.G == 2 ? 3 : 2;  // index pass + two decode instances / entropy + prediction
+        if (launches) *launches += plan.G == 2 ? 5 : 2;  // index pass + four decode instances / entropy + prediction
     } else {
         decode_frames_kernel<12><<<grid, block, 0, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results,
                                                              d_need_hi, nullptr, 0);

@@ -457,12 +457,16 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
 // an 8-tap and a 12-tap body: every warp of a batch of mixed orders runs at once), GROUP 1 the warps with orders
 // up to 32 (non-subset streams), whose body needs half as many registers again.  A warp does its work in the
 // instance of its group and leaves the other at once.
-template <int GROUP>
+//
+// WIDE = true is the second chance of frames whose samples left the range the i32 accumulator is exact for (see
+// below): the same rows once more with the reference's i64 arithmetic only.  It looks at nothing unless the first
+// pass raised `need_wide`.
+template <int GROUP, bool WIDE>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
                         uint32_t n_frames, int32_t* __restrict__ out, clx_frame_result* __restrict__ results,
                         const SeqParams* __restrict__ params, uint32_t CH, uint32_t ch_log2, uint32_t n_pwarps,
-                        int* __restrict__ need_generic) {
+                        int* __restrict__ need_generic, int* __restrict__ need_wide) {
     __shared__ __align__(8192) int32_t s_tile[DEC_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
     __shared__ SeqRow s_rows[DEC_WARPS][32];
     __shared__ __align__(16) int32_t* s_outp[DEC_WARPS][32];
@@ -471,6 +475,7 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t pw = blockIdx.x * DEC_WARPS + warp;  // CH subframe warps per group of 32 frames
     if (pw >= n_pwarps) return;
+    if (WIDE && *need_wide == 0) return;
     const uint32_t w = pw >> ch_log2, part = pw & (CH - 1);
     const uint32_t j = part * (32u >> ch_log2) + (lane >> ch_log2);  // frame within the group
     const uint32_t c = lane & (CH - 1);
@@ -485,7 +490,7 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][lane][0]);
     L.rc.io.open_idle(ring, lane, bytes);
     L.init_idle();
-    if (f < n_frames && results[f].status == CLX_OK) {
+    if (f < n_frames && results[f].status == (WIDE ? (int32_t)CLX_INTERNAL_NEED_WIDE : (int32_t)CLX_OK)) {
         const clx_frame_desc d = descs[f];
         if (c < d.n_channels) {
             sp = params + (size_t)f * CH + c;
@@ -511,10 +516,6 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     const uint32_t max_order = __reduce_max_sync(0xffffffffu, active ? order : 0u);
     const int cls = max_order <= 8 ? 0 : max_order <= 12 ? 1 : 2;
     if ((cls == 2) != (GROUP == 1)) return;
-    if (active) {
-        L.rc.io.open(ring, lane, bytes, buf_bytes, descs[f].byte_offset);
-        L.init(*sp, bs, bit0 + byte_len * 8);
-    }
     const bool vec_own = (reinterpret_cast<uintptr_t>(sub) & 15) == 0;
     const bool all_vec = __all_sync(0xffffffffu, !active || vec_own);
     SeqRow* pr = s_rows[warp];
@@ -543,12 +544,24 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     // straight-line flush variants only where they pay: the i32-accumulator bodies (16-bit audio)
 #define CLX_BODY(T, UU)                                    \
     do {                                                   \
-        if (all_narrow) {                                  \
+        if (!WIDE && narrow) {                             \
             if (fmode == 2) CLX_ROWS(T, UU, int, 2);       \
             else if (fmode == 1) CLX_ROWS(T, UU, int, 1);  \
             else CLX_ROWS(T, UU, int, 0);                  \
         } else CLX_ROWS(T, UU, long long, 0);              \
     } while (0)
+    // The i32 accumulator is exact only while sum|coef| * max|sample| < 2^31, which is checked against the samples
+    // actually produced.  Streams that keep to their nominal sample width never fail it; a frame whose samples do
+    // leave that range is decoded once more by the WIDE instance (the reference's i64 arithmetic).
+    const bool narrow = !WIDE && all_narrow;
+    if (WIDE) {
+        if (active && c == 0) results[f].status = CLX_OK;  // this pass's verdict replaces the first one's
+        __syncwarp();
+    }
+    if (active) {
+        L.rc.io.open(ring, lane, bytes, buf_bytes, descs[f].byte_offset);
+        L.init(*sp, bs, bit0 + byte_len * 8);
+    }
     if (GROUP == 1) CLX_BODY(32, 4);
     else if (cls == 0) CLX_BODY(8, 8);
     else CLX_BODY(12, 4);
@@ -564,16 +577,17 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
         if (consumed > byte_len) redo = true;
         else results[f].consumed = consumed;
     }
-    // The shortcuts taken above are exact only under conditions on the samples actually produced:
-    //  * i32 accumulator: sum|coef| * max|sample| < 2^31;
-    //  * mid/side without the wrapping intermediate: max|sample| << wasted < 2^29 on both channels.
-    // A frame that fails either is re-decoded by the generic kernel (it never happens in a valid stream).
+    // The mid/side shortcut (no wrapping intermediate) is exact only while max|sample| << wasted < 2^29 on both
+    // channels, again checked on the samples produced; a frame that fails is re-decoded by the generic kernel.
     const uint32_t m = max((uint32_t)smax, 0u - (uint32_t)smin);
-    if (all_narrow && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) redo = true;
+    if (narrow && order > 0 && (unsigned long long)absum * m >= (1ull << 31)) {
+        if (!redo) results[f].status = CLX_INTERNAL_NEED_WIDE;  // (a frame that needs the generic kernel anyway keeps that mark)
+        *need_wide = 1;
+    }
     if (ca == 10 && (((unsigned long long)m) << wasted) >= (1ull << 29)) redo = true;
     if (redo) {
-        results[f].status = CLX_INTERNAL_NEED_GENERIC;  // benign race: every writer stores the same value
-        *need_generic = 1;
+        results[f].status = CLX_INTERNAL_NEED_GENERIC;  // takes precedence over NEED_WIDE whatever the order of the writes:
+        *need_generic = 1;                              // the WIDE pass only picks up frames still marked NEED_WIDE
     }
 }
 
@@ -613,8 +627,8 @@ cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fra
 #else
         const size_t dyn = 0;
 #endif
-#define CLX_DEC(C) decode_subframes_kernel<C><<<g2, b2, dyn, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic)
-        CLX_DEC(0); CLX_DEC(1);
+#define CLX_DEC(C, W) decode_subframes_kernel<C, W><<<g2, b2, dyn, stream>>>(d_bytes, buf_bytes, d_descs, n_frames, d_out, d_results, params, CH, ch_log2, n_pwarps, d_need_generic, d_need_generic + 2)
+        CLX_DEC(0, false); CLX_DEC(1, false); CLX_DEC(0, true); CLX_DEC(1, true);
 #undef CLX_DEC
     }
     return cudaGetLastError();

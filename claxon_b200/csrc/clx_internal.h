@@ -11,6 +11,8 @@
 // Device-only marker: the cooperative kernel declined the frame (anything irregular: malformed
 // input, escape codes, oversize frames ...); the generic lane-per-frame kernel decodes it.
 #define CLX_INTERNAL_NEED_GENERIC (-2)
+// Device-only marker of the throughput path: decode the frame again with the i64 accumulator (clx_fused.cu).
+#define CLX_INTERNAL_NEED_WIDE (-3)
 
 namespace clx {
 struct CoopPlan {          // whether / how a batch uses the fast path
@@ -40,6 +42,9 @@ cudaError_t launch_coop(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_fr
 cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs,
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
                           void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
+// clx_crc.cu: frame CRC-16 of every frame that decoded (over the length the decode found), on the device
+cudaError_t launch_crc16(const uint8_t* d_bytes, const clx_frame_desc* d_descs, uint32_t n_frames, clx_frame_result* d_results,
+                         cudaStream_t stream);
 // clx_output.cu: planar i32 -> interleaved little-endian samples (CLX_OUT_* modes), frame by frame
 uint32_t output_elem_size(uint32_t mode);
 cudaError_t launch_interleave(const clx_frame_desc* d_descs, uint32_t n_frames, uint32_t max_frame_elems, const int32_t* d_planar,
