@@ -19,11 +19,12 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
+from ._lib import (OPEN_METADATA_ONLY, OPEN_NO_VORBIS_COMMENT)
 from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL_ONLY, OPT_WARP_PER_FRAME, OPT_LANE_PER_FRAME,
                    FRAME_VARIABLE_BLOCKING, FRAME_CRC16_VERIFIED,
                    OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24)
 
-__all__ = ["Error", "Block", "FrameReader", "FlacReader", "StreamInfo", "Context", "DeviceBatch",
+__all__ = ["Error", "Block", "FrameReader", "FlacReader", "FlacReaderOptions", "StreamInfo", "Context", "DeviceBatch",
            "parse_frame_header", "demux_frames", "open_stream", "status_str", "DESC_DTYPE", "RESULT_DTYPE"]
 
 # numpy views of the C structs (same layout; asserted below)
@@ -428,39 +429,115 @@ class FrameReader:
             pass
 
 
+@dataclass
+class FlacReaderOptions:
+    """claxon::FlacReaderOptions (src/lib.rs:123-151)."""
+    metadata_only: bool = False
+    read_vorbis_comment: bool = True
+
+
+def _parse_vorbis_comment(body: np.ndarray):
+    """(vendor, [(comment, separator index)]) of a validated VORBIS_COMMENT body (src/metadata.rs:402-513)."""
+    raw = body.tobytes()
+    at = 4 + int.from_bytes(raw[0:4], "little")
+    vendor = raw[4:at].decode("utf-8")
+    count = int.from_bytes(raw[at:at + 4], "little")
+    at += 4
+    comments = []
+    while len(raw) - at >= 4 and len(comments) < count:
+        n = int.from_bytes(raw[at:at + 4], "little")
+        at += 4
+        if n == 0:  # zero-length comments occur in the wild and are skipped
+            count -= 1
+            continue
+        c = raw[at:at + n]
+        at += n
+        comments.append((c.decode("utf-8"), c.index(b"=")))
+    return vendor, comments
+
+
 class FlacReader:
     """claxon::FlacReader (src/lib.rs:207-470) for in-memory streams / files."""
 
-    def __init__(self, data, ctx: Context | None = None):
-        self._frames = FrameReader(data, ctx, _flac=True)
+    def __init__(self, data, ctx: Context | None = None, options: FlacReaderOptions | None = None):
+        self._options = options or FlacReaderOptions()
+        buf = _as_u8(data)
+        flags = ((OPEN_METADATA_ONLY if self._options.metadata_only else 0)
+                 | (0 if self._options.read_vorbis_comment else OPEN_NO_VORBIS_COMMENT))
         si = _lib.StreamInfoC()
-        _check(self._frames._ctx._L.clx_reader_streaminfo(self._frames._h, C.byref(si)))
+        first, vc_off, vc_len = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        _check(_lib.load().clx_open_stream_ex(buf.ctypes.data, buf.size, flags, C.byref(si), C.byref(first),
+                                              C.byref(vc_off), C.byref(vc_len)))
         self._si = StreamInfo._from_c(si)
+        self._vendor, self._comments = None, []
+        if vc_len.value:
+            self._vendor, self._comments = _parse_vorbis_comment(buf[vc_off.value:vc_off.value + vc_len.value])
+        # FlacReaderState::Full / MetadataOnly (src/lib.rs:96-104)
+        self._frames = None if self._options.metadata_only else FrameReader(buf, ctx, _flac=True)
 
     @classmethod
     def new(cls, data, ctx: Context | None = None) -> "FlacReader":
         return cls(data, ctx)
 
     @classmethod
+    def new_ext(cls, data, options: FlacReaderOptions, ctx: Context | None = None) -> "FlacReader":
+        return cls(data, ctx, options)
+
+    @classmethod
     def open(cls, path, ctx: Context | None = None) -> "FlacReader":
         with open(path, "rb") as f:
             return cls(f.read(), ctx)
 
+    @classmethod
+    def open_ext(cls, path, options: FlacReaderOptions, ctx: Context | None = None) -> "FlacReader":
+        with open(path, "rb") as f:
+            return cls(f.read(), ctx, options)
+
     def streaminfo(self) -> StreamInfo:
         return self._si
 
-    def blocks(self) -> FrameReader:
+    def vendor(self) -> str | None:
+        """Vendor string of the Vorbis comment block, if present (src/lib.rs:318-325)."""
+        return self._vendor
+
+    def tags(self):
+        """(name, value) pairs of the Vorbis comments, names as stored (src/lib.rs:327-345)."""
+        return [(c[:i], c[i + 1:]) for c, i in self._comments]
+
+    def get_tag(self, tag_name: str):
+        """Values of every comment whose name equals tag_name ASCII-case-insensitively (src/lib.rs:347-360)."""
+        def lower(t):
+            return "".join(chr(ord(ch) + 32) if "A" <= ch <= "Z" else ch for ch in t)
+        return [c[i + 1:] for c, i in self._comments if lower(c[:i]) == lower(tag_name)]
+
+    def _full(self, what: str) -> FrameReader:
+        if self._frames is None:  # the reference panics
+            raise RuntimeError(f"FlacReaderOptions::metadata_only must be false to be able to use FlacReader::{what}()")
         return self._frames
 
-    def samples(self):
-        """FlacSamples (src/lib.rs:473-519): interleaved samples; raises once on a bad frame."""
-        buffer = None
+    def blocks(self) -> FrameReader:
+        return self._full("blocks")
+
+    def samples(self, batch_frames: int = 256):
+        """FlacSamples (src/lib.rs:473-519): interleaved samples, channel by channel for each inter-channel
+        sample; an error surfaces once, where the bad frame starts, after every sample before it.  Frames are
+        decoded `batch_frames` at a time on the device."""
+        return self._iter_samples(self._full("samples"), batch_frames)
+
+    def into_samples(self, batch_frames: int = 256):
+        """FlacIntoSamples (src/lib.rs:412-435): as samples(), taking the reader with it."""
+        frames, self._frames = self._full("into_samples"), None
+        return self._iter_samples(frames, batch_frames)
+
+    @staticmethod
+    def _iter_samples(frames: FrameReader, batch_frames: int):
         while True:
-            block = self._frames.read_next_or_eof(buffer)
-            if block is None:
+            blocks = frames.read_batch(batch_frames)  # raises if the very next frame is bad
+            if not blocks:
                 return
-            ch, bs = block.channels(), block.duration()
-            inter = block.into_buffer().reshape(ch, bs).T.reshape(-1)
-            for v in inter:
-                yield int(v)
-            buffer = block.into_buffer()
+            for block in blocks:
+                ch, bs = block.channels(), block.duration()
+                yield from block.into_buffer().reshape(ch, bs).T.reshape(-1).tolist()
+
+    def into_inner(self):
+        return self._frames.into_inner() if self._frames is not None else None

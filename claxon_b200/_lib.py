@@ -45,6 +45,7 @@ OPT_NO_VERIFY_CRC = 1
 OPT_GENERIC_KERNEL_ONLY = 2
 OPT_WARP_PER_FRAME = 4
 OPT_LANE_PER_FRAME = 8
+OPEN_METADATA_ONLY, OPEN_NO_VORBIS_COMMENT = 1, 2
 OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24 = 0, 1, 2, 3
 FRAME_VARIABLE_BLOCKING = 1
 FRAME_CRC16_VERIFIED = 2
@@ -57,6 +58,8 @@ SYMBOLS = {
     "clx_abi_version": (C.c_uint32, []),
     "clx_parse_frame_header": (C.c_int, [_u8p, _sz, C.POINTER(FrameDesc), C.c_uint32]),
     "clx_open_stream": (C.c_int, [_u8p, _sz, C.POINTER(StreamInfoC), C.POINTER(C.c_uint64)]),
+    "clx_open_stream_ex": (C.c_int, [_u8p, _sz, C.c_uint32, C.POINTER(StreamInfoC), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "clx_demux_frames": (_sz, [_u8p, _sz, C.c_uint64, _vp, _sz, C.POINTER(C.c_uint64),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_uint32]),
     "clx_crc8": (C.c_uint8, [_u8p, _sz]),

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "claxon_b200.h"
 #include "clx_internal.h"
 #include "clx_lanes.h"
@@ -73,6 +75,12 @@ struct DeviceIO {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    // Before a read of at most 64 bytes from bitpos on (a header field, a single code, a window seat): nothing to
+    // do if the steady-state refill is far enough ahead — what lies that far behind its front has landed, by the
+    // wait of the last prefetch_group() — else a blocking refill.
+    __device__ __forceinline__ void ensure_near(uint32_t bitpos) {
+        if (fq < (bitpos >> 7) + 4u + WAITN) ensure(bitpos);
     }
     // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads (C2: 0.36 on
     // average): one predicated copy per group keeps the ring ahead of light streams, a second one — behind a
@@ -418,7 +426,10 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
                 have_drain = true;
             }
         };
-        auto step = [&](const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
+        // MP: some subframe of the warp has a partition boundary ahead (its own instance of the loop, so that warps
+        // of single-partition subframes do not even look)
+        auto step = [&](auto mp, const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
+            if (decltype(mp)::value && active && !L.fast()) L.quick_prepare();  // a partition header, from the window
             // codes per window refill: what every lane on the fast path allows (by its partition's Rice parameter)
             const uint32_t nc = __reduce_min_sync(0xffffffffu, L.spec_cap());
             bool good;
@@ -429,16 +440,20 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
         };
         if (active) produce(rA, true);
         uint32_t t = head_end;
-        while (t + 16 < bulk_end) {
-            step(rA, rB, t);
-            step(rB, rA, t + 8);
-            t += 16;
-        }
-        if (t + 8 < bulk_end) {
-            step(rA, rB, t);
-            t += 8;
-            consume(rB, t);
-        } else consume(rA, t);
+        auto run = [&](auto mp) {
+            while (t + 16 < bulk_end) {
+                step(mp, rA, rB, t);
+                step(mp, rB, rA, t + 8);
+                t += 16;
+            }
+            if (t + 8 < bulk_end) {
+                step(mp, rA, rB, t);
+                t += 8;
+                consume(rB, t);
+            } else consume(rA, t);
+        };
+        if (__any_sync(0xffffffffu, active && L.rc.parts_left != 0)) run(std::true_type{});
+        else run(std::false_type{});
         after(t);
         if (have_drain) {  // whatever of the last full tile has not been written yet (re-writing a quarter is harmless)
             const uint32_t g0 = (bulk_end & ~31u) - 32;

@@ -250,6 +250,20 @@ int clx_parse_frame_header(const uint8_t* p, size_t n, clx_frame_desc* d, uint32
 
 // FlacReader::new_ext with default options (src/lib.rs:230-307) on a byte span.
 int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* first_frame) {
+    return clx_open_stream_ex(p, n, 0, si, first_frame, nullptr, nullptr);
+}
+
+// FlacReader::new_ext (src/lib.rs:230-307) with FlacReaderOptions (src/lib.rs:123-170): the metadata walk stops
+// as soon as every desired block has been read (`opts_current.has_desired_blocks()`), and a Vorbis comment
+// block that was read but not asked for is dropped again.
+int clx_open_stream_ex(const uint8_t* p, size_t n, uint32_t open_flags, clx_streaminfo* si, uint64_t* first_frame,
+                       uint64_t* vc_offset, uint32_t* vc_length) {
+    const bool metadata_only = (open_flags & CLX_OPEN_METADATA_ONLY) != 0;
+    bool want_vc = !(open_flags & CLX_OPEN_NO_VORBIS_COMMENT);  // opts_current.read_vorbis_comment
+    const bool keep_vc = want_vc;
+    if (vc_offset) *vc_offset = 0;
+    if (vc_length) *vc_length = 0;
+    if (first_frame) *first_frame = 0;
     memset(si, 0, sizeof *si);
     if (n < 4) return CLX_ERR_IO_UNEXPECTED_EOF;
     const uint32_t magic = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
@@ -257,6 +271,7 @@ int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* fi
         return (magic & 0xffffff00u) == 0x49443300u ? CLX_ERR_STREAM_HEADER_ID3 : CLX_ERR_STREAM_HEADER_INVALID;
     size_t at = 4;
     bool first = true, have_vc = false;
+    bool first_block_only_seen = true;  // only the streaminfo block has been handled so far
     for (;;) {
         if (at + 4 > n) return CLX_ERR_IO_UNEXPECTED_EOF;  // block header, src/metadata.rs:214-231
         const bool is_last = (p[at] >> 7) != 0;
@@ -299,6 +314,10 @@ int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* fi
         case 4:
             st = check_vorbis(body, avail, length);
             is_vc = true;
+            if (st == CLX_OK && keep_vc) {
+                if (vc_offset) *vc_offset = at;
+                if (vc_length) *vc_length = length;
+            }
             break;
         case 127:
             st = CLX_ERR_METADATA_BLOCK_TYPE;
@@ -315,13 +334,18 @@ int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* fi
             if (is_vc) {
                 if (have_vc) return CLX_ERR_SECOND_VORBIS_COMMENT;
                 have_vc = true;
+                want_vc = false;  // "We have one, no new one is desired."
             }
             if (is_si) return CLX_ERR_SECOND_STREAMINFO;
         }
         at += length;
         if (is_last) break;
+        // early-out once all desired blocks have been collected (src/lib.rs:275-279; the reference makes this
+        // test after every block that follows the streaminfo block)
+        if (!first_block_only_seen && metadata_only && !want_vc) return CLX_OK;
+        first_block_only_seen = false;
     }
-    *first_frame = at;
+    if (first_frame) *first_frame = metadata_only ? 0 : at;
     return CLX_OK;
 }
 

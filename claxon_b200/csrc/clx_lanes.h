@@ -113,6 +113,7 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 //   void ensure(uint32_t bitpos)          the bits from bitpos on (ring size minus slack) are readable through word()
 //   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: ensure() before reading on
 //   void seek_next(uint32_t wi), uint32_t next_raw()   sequential word reads, bytes as stored (the register window's refill)
+//   void ensure_near(uint32_t bitpos)     cheap: the next 64 bytes from bitpos are readable (refills, blocking, only if not)
 
 // ---------------------------------------------------------------------------------
 // Bit window + Rice partition state shared by both lanes
@@ -137,6 +138,7 @@ struct RiceCursor {
     uint32_t ncap;        // codes per window refill this partition allows: 2 or 1
     uint32_t n_fast;      // groups of eight codes the fast path may take before anything else has to happen
     bool ok, first_part;
+    bool wvalid;          // W0..W2 are seated at the cursor (so single codes and partition headers can use them)
 
     CLX_HD void reset(uint32_t start_bit, uint32_t limit_bit) {
         o = start_bit; limit = limit_bit;
@@ -144,19 +146,26 @@ struct RiceCursor {
         n_left = 0; parts_left = 0; per = 0; order = 0; pbits = 4;
         k = 0; Kneg = 0xffffffffu; K30 = 30; ncap = 1;
         n_fast = 0;
-        ok = true; first_part = false;
+        ok = true; first_part = false; wvalid = false;
     }
-    CLX_HD void fail() { ok = false; n_left = 0; parts_left = 0; n_fast = 0; }
+    CLX_HD void fail() { ok = false; n_left = 0; parts_left = 0; n_fast = 0; wvalid = false; }
     CLX_HD uint32_t peek32(uint32_t pos) { return hd_fsl(io.word(pos >> 5), io.word((pos >> 5) + 1), pos); }
     CLX_HD uint32_t bits(uint32_t pos, uint32_t n) { return n ? peek32(pos) >> (32 - n) : 0u; }  // n <= 32
     // Seats the register window at the cursor and opens the fast path for the rest of the partition.
     CLX_HD void window_seek() {
-        io.ensure(o);
+        io.ensure_near(o);
         const uint32_t wi = o >> 5;
         W0 = io.word(wi); W1 = io.word(wi + 1);
         io.seek_next(wi + 2);
         W2 = io.next_raw();
         n_fast = n_left >> 3;
+        wvalid = true;
+    }
+    // Moves the seated window forward by n bits (n <= 32).
+    CLX_HD void window_advance(uint32_t n) {
+        const uint32_t on = o + n;
+        if ((on ^ o) & 32u) { W0 = W1; W1 = hd_bswap(W2); W2 = io.next_raw(); }
+        o = on;
     }
 
     // residual header (src/subframe.rs:236-304) at the cursor; `bs` = block size, `ord` = predictor order
@@ -176,14 +185,19 @@ struct RiceCursor {
         first_part = true;
         n_left = 0;
         n_fast = 0;
+        wvalid = false;
     }
     // partition header (src/subframe.rs:310-319, :358-367)
     CLX_HD void do_part() {
-        io.ensure(o);
+        io.ensure_near(o);
         k = bits(o, pbits);
         o += pbits;
         n_fast = 0;
+        wvalid = false;
         if (k == (1u << pbits) - 1u) { fail(); return; }  // escape code: Unsupported in the reference
+        set_parameter();
+    }
+    CLX_HD void set_parameter() {
         n_left = first_part ? per - order : per;
         first_part = false;
         parts_left--;
@@ -192,6 +206,16 @@ struct RiceCursor {
         Kneg = 0u - K;
         ncap = k <= PAIR_KMAX ? 2u : 1u;
         if (o > limit) fail();
+    }
+    // The next partition's header straight from the seated window — the common way from one partition to the
+    // next: no shared-memory round trip, the window stays seated and the fast path open.  Precondition: wvalid,
+    // n_left == 0, parts_left != 0, not the first partition.
+    CLX_HD void quick_part() {
+        k = hd_fsl(W0, W1, o) >> (32u - pbits);
+        window_advance(pbits);
+        if (k == (1u << pbits) - 1u) { fail(); return; }
+        set_parameter();
+        n_fast = n_left >> 3;
     }
     // Moves to the partition that holds the next residual (empty partitions still carry a parameter,
     // src/subframe.rs:283-288).  False: nothing left, or failed.
@@ -205,8 +229,12 @@ struct RiceCursor {
     // Called when n_fast == 0 and a group of eight is wanted: partition switch and window seat.
     CLX_HD void prepare() {
         if (!ok) return;
-        if (n_left == 0 && parts_left != 0) settle();
-        if (ok && n_left >= 8) window_seek();
+        if (n_left == 0 && parts_left != 0) {
+            if (wvalid && !first_part) { quick_part(); if (n_left != 0 || !ok) return; }  // (an empty partition: the slow way)
+            settle();
+        }
+        if (ok && n_left >= 8 && !wvalid) window_seek();
+        else if (ok && wvalid) n_fast = n_left >> 3;
     }
 
     // (q << k) | r of the code whose 32-bit window is `hi` with its terminator at bit m = sh + k, then
@@ -263,7 +291,7 @@ struct RiceCursor {
             io.seek_next((o0 >> 5) + 3);
             bad = codes8<1, VALUES>(e);
         }
-        if (bad) { o = o0; n_fast = 0; return false; }
+        if (bad) { o = o0; n_fast = 0; wvalid = false; return false; }
         n_left -= 8;
         n_fast--;
         return true;
@@ -288,11 +316,27 @@ struct RiceCursor {
         o = good ? o : o0;
         n_left = good ? n_left - 8 : n_left;
         n_fast = good ? n_fast - 1 : 0u;
+        wvalid = good;  // a group that does not count has moved the registers but not the cursor
         return good;
+    }
+    // ---- one Rice code (precondition n_left > 0): from the seated window when it fits, else the long way ----
+    template <bool VALUES>
+    CLX_HD int32_t one_code() {
+        if (!wvalid) window_seek();
+        else io.ensure_near(o);
+        const uint32_t x = hd_fsl(W0, W1, o);
+        const uint32_t sh = hd_msb(x) - k;
+        if ((int32_t)sh < 0) return slow_code();  // longer than the window
+        const int32_t e = VALUES ? code_value(x, sh) : 0;
+        window_advance(32u - sh);
+        n_left--;
+        n_fast = n_left >> 3;
+        return e;
     }
     // ---- one Rice code of any shape; precondition n_left > 0 ----
     CLX_HD int32_t slow_code() {
         n_fast = 0;
+        wvalid = false;
         uint32_t q = 0;
         uint32_t v;
         for (;;) {
@@ -459,13 +503,22 @@ struct IndexLane {
     CLX_HD void slow_step() {
         if (mode == SEQ_SUBFRAME) { do_subframe(); return; }
         if (mode != SEQ_RUN) return;
-        if (!rc.settle()) {
+        if (rc.n_left == 0) {  // next partition (or the end of the subframe's residual)
+            if (rc.parts_left != 0 && rc.wvalid && !rc.first_part) rc.quick_part();
+            if (rc.ok && rc.n_left == 0 && !rc.settle()) {
+                if (!rc.ok) { fail(); return; }
+                end_of_body();
+                return;
+            }
             if (!rc.ok) { fail(); return; }
-            end_of_body();
-            return;
+            if (rc.n_fast != 0 && slow_budget == 0) return;  // next step: a fast group
         }
-        if (slow_budget == 0 && rc.n_left >= 8) { rc.window_seek(); return; }  // next step: a fast group
-        rc.slow_code();
+        if (slow_budget == 0 && rc.n_left >= 8) {
+            if (!rc.wvalid) rc.window_seek();
+            else rc.n_fast = rc.n_left >> 3;
+            return;  // next step: a fast group
+        }
+        rc.template one_code<false>();  // the last few codes of a partition, or a stretch after a group that failed
         if (slow_budget) slow_budget--;
         if (!rc.ok) { fail(); return; }
         if (rc.n_left == 0 && rc.parts_left == 0) end_of_body();
@@ -495,6 +548,10 @@ struct SubLane {
     // A group of eight residuals: `if (!fast()) prepare(); if (fast()) got = fast_group(e); if (!got) eight next()`.
     CLX_HD bool fast() const { return rc.n_fast != 0; }
     CLX_HD void prepare() { if (kind == SUB_PREDICTED) rc.prepare(); }
+    // The cheap part of prepare(), for the top of a trip: the next partition's header from the seated window.
+    CLX_HD void quick_prepare() {
+        if (kind == SUB_PREDICTED && rc.ok && rc.wvalid && rc.n_left == 0 && rc.parts_left != 0 && !rc.first_part) rc.quick_part();
+    }
     CLX_HD bool fast_group(int32_t (&e)[8]) { return rc.fast_group(e); }
     // codes per refill spec_group may use for this lane (a lane off the fast path does not care)
     CLX_HD uint32_t spec_cap() const { return rc.n_fast == 0 ? 2u : rc.ncap; }
@@ -510,8 +567,12 @@ struct SubLane {
             if (rc.o > rc.limit) { rc.fail(); return 0; }
             return v;
         }
-        if (!rc.settle()) { rc.fail(); return 0; }  // more residuals asked for than the partitions hold
-        return rc.slow_code();
+        if (rc.n_left == 0) {
+            if (rc.parts_left != 0 && rc.wvalid && !rc.first_part) rc.quick_part();
+            if (rc.ok && rc.n_left == 0 && !rc.settle()) { rc.fail(); return 0; }  // more residuals asked for than the partitions hold
+            if (!rc.ok) return 0;
+        }
+        return rc.template one_code<true>();
     }
     // After the last residual: the subframe must end inside the frame.  Returns the end bit.
     CLX_HD uint32_t finish() {

@@ -107,6 +107,17 @@ int clx_parse_frame_header(const uint8_t* p, size_t n, clx_frame_desc* d, uint32
 /* FlacReader::new (src/lib.rs:217-307, default options): checks 'fLaC', walks the
  * metadata blocks, returns STREAMINFO and the offset of the first frame. */
 int clx_open_stream(const uint8_t* p, size_t n, clx_streaminfo* si, uint64_t* first_frame);
+/* FlacReader::new_ext with FlacReaderOptions (src/lib.rs:123-170, :230-307).  CLX_OPEN_METADATA_ONLY: stop
+ * as soon as every desired block has been read; *first_frame is then 0 and the stream cannot be decoded
+ * (claxon panics in blocks()/samples()).  CLX_OPEN_NO_VORBIS_COMMENT == read_vorbis_comment: false.
+ * *vc_offset / *vc_length locate the body of the (validated) VORBIS_COMMENT block, 0 / 0 when there is
+ * none or it was not asked for: little-endian u32 vendor length, vendor string, u32 comment count, then
+ * per comment a u32 length and "NAME=value" in UTF-8 (what FlacReader::vendor/tags/get_tag expose,
+ * src/lib.rs:318-360, src/metadata.rs:134-211); zero-length comments are to be skipped. */
+#define CLX_OPEN_METADATA_ONLY 1u
+#define CLX_OPEN_NO_VORBIS_COMMENT 2u
+int clx_open_stream_ex(const uint8_t* p, size_t n, uint32_t open_flags, clx_streaminfo* si, uint64_t* first_frame,
+                       uint64_t* vc_offset, uint32_t* vc_length);
 
 /* Frame demultiplexer: finds frame boundaries in bytes[start..n) without decoding:
  * sync code + header parse + CRC-8, then the first later sync position at which the

