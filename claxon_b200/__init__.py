@@ -241,19 +241,30 @@ class Context:
     def upload(self, data, descs: np.ndarray, out_elems: int) -> "DeviceBatch":
         return DeviceBatch(self, data, descs, out_elems)
 
+    def adopt(self, device_ptr: int, nbytes: int, descs: np.ndarray, out_elems: int) -> "DeviceBatch":
+        """A batch whose frame bytes already sit in this GPU's memory at `device_ptr` (e.g. a torch tensor's
+        data_ptr() after the NCCL scatter of claxon_b200.shard.scatter_batch): copied device to device."""
+        return DeviceBatch(self, None, descs, out_elems, device_ptr=device_ptr, nbytes=nbytes)
+
 
 class DeviceBatch:
     """clx_batch: frames resident in HBM; decode() launches the kernels only."""
 
-    def __init__(self, ctx: Context, data, descs: np.ndarray, out_elems: int):
+    def __init__(self, ctx: Context, data, descs: np.ndarray, out_elems: int, device_ptr: int | None = None,
+                 nbytes: int = 0):
         self.ctx = ctx
-        buf = _as_u8(data)
         self.descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
         self.out_elems = int(out_elems)
-        self.nbytes = int(buf.size)
         h = C.c_void_p()
-        _check(ctx._L.clx_batch_create(ctx._h, buf.ctypes.data, buf.size, self.descs.ctypes.data,
-                                       self.descs.size, self.out_elems, C.byref(h)), ctx)
+        if device_ptr is None:
+            buf = _as_u8(data)
+            self.nbytes = int(buf.size)
+            _check(ctx._L.clx_batch_create(ctx._h, buf.ctypes.data, buf.size, self.descs.ctypes.data,
+                                           self.descs.size, self.out_elems, C.byref(h)), ctx)
+        else:
+            self.nbytes = int(nbytes)
+            _check(ctx._L.clx_batch_create_ex(ctx._h, device_ptr, self.nbytes, self.descs.ctypes.data, self.descs.size,
+                                              self.out_elems, _lib.BATCH_BYTES_ON_DEVICE, C.byref(h)), ctx)
         self._h = h
 
     def decode(self, stream: int = 0):

@@ -46,6 +46,7 @@ OPT_GENERIC_KERNEL_ONLY = 2
 OPT_WARP_PER_FRAME = 4
 OPT_LANE_PER_FRAME = 8
 OPEN_METADATA_ONLY, OPEN_NO_VORBIS_COMMENT = 1, 2
+BATCH_BYTES_ON_DEVICE = 1
 OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24 = 0, 1, 2, 3
 FRAME_VARIABLE_BLOCKING = 1
 FRAME_CRC16_VERIFIED = 2
@@ -70,6 +71,7 @@ SYMBOLS = {
     "clx_decode_frames": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _vp, _sz, _vp]),
     "clx_decode_frames_to": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _vp, _sz, _vp, C.c_uint32]),
     "clx_batch_create": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _sz, C.POINTER(_vp)]),
+    "clx_batch_create_ex": (C.c_int, [_vp, _u8p, _sz, _vp, _sz, _sz, C.c_uint32, C.POINTER(_vp)]),
     "clx_batch_decode": (C.c_int, [_vp, _vp, C.c_uint32]),
     "clx_batch_sync": (C.c_int, [_vp, _vp]),
     "clx_batch_read": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),

@@ -141,6 +141,7 @@ struct clx_batch {
     std::vector<uint64_t> h_offset;
     std::vector<uint32_t> h_len;
     std::vector<uint32_t> order;   // device position -> caller's frame index (empty: identity), see shape_order()
+    bool device_crc = false;       // bytes came from device memory: the CRC-16 check runs on the device, inside the graph
 };
 
 namespace {
@@ -461,7 +462,13 @@ int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, cons
 // ---------------------------------------------------------------------------------
 int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs, size_t n_frames,
                      size_t out_elems, clx_batch** out) {
+    return clx_batch_create_ex(ctx, bytes, nbytes, descs, n_frames, out_elems, 0, out);
+}
+
+int clx_batch_create_ex(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs, size_t n_frames,
+                        size_t out_elems, uint32_t batch_flags, clx_batch** out) {
     if (!ctx || !out || (!bytes && nbytes) || (!descs && n_frames)) return CLX_ERR_INVALID_ARGUMENT;
+    const bool on_device = (batch_flags & CLX_BATCH_BYTES_ON_DEVICE) != 0;
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
     for (size_t i = 0; i < n_frames; i++)
@@ -479,7 +486,7 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_results, std::max<size_t>(1, n_frames) * sizeof(clx_frame_result));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_need_hi, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_params, clx::coop_params_bytes(b->plan, b->n_frames) + 16);
-    if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_bytes, bytes, nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         if (shape_order(descs, 0, n_frames, b->order)) {
             std::vector<clx_frame_desc> sorted(n_frames);
@@ -494,8 +501,11 @@ int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const cl
         return cuda_fail(ctx, e, "clx_batch_create");
     }
     if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {
-        precompute_crc(ctx, bytes, descs, n_frames);
-        b->crc_ok = ctx->crc_verdict;
+        if (on_device) b->device_crc = true;  // no host copy to checksum: clx_crc.cu, as part of every decode
+        else {
+            precompute_crc(ctx, bytes, descs, n_frames);
+            b->crc_ok = ctx->crc_verdict;
+        }
     }
     b->h_offset.resize(n_frames);
     b->h_len.resize(n_frames);
@@ -522,6 +532,7 @@ void build_graph(clx_ctx* ctx, clx_batch* b) {
     if (e == cudaSuccess) {
         cudaError_t e1 = clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results,
                                             b->d_need_hi, b->d_params, b->plan, st, &n);
+        if (e1 == cudaSuccess && b->device_crc) { e1 = clx::launch_crc16(b->d_bytes, b->d_descs, b->n_frames, b->d_results, st); n++; }
         e = cudaStreamEndCapture(st, &g);
         if (e1 != cudaSuccess) e = e1;
     }
@@ -544,6 +555,7 @@ int enqueue_batch(clx_ctx* ctx, clx_batch* b, cudaStream_t st) {
     if (b->ev_idle) CU(ctx, cudaStreamWaitEvent(st, b->ev_idle, 0));
     CU(ctx, clx::launch_decode(b->d_bytes, b->buf_bytes, b->d_descs, b->n_frames, b->d_out, b->d_results, b->d_need_hi,
                                b->d_params, b->plan, st, &ctx->launches));
+    if (b->device_crc) { CU(ctx, clx::launch_crc16(b->d_bytes, b->d_descs, b->n_frames, b->d_results, st)); ctx->launches++; }
     if (!b->ev_idle) CU(ctx, cudaEventCreateWithFlags(&b->ev_idle, cudaEventDisableTiming));
     CU(ctx, cudaEventRecord(b->ev_idle, st));
     return CLX_OK;
@@ -589,7 +601,7 @@ int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, c
             CU(ctx, cudaMemcpy(dev.data(), b->d_results, b->n_frames * sizeof(clx_frame_result), cudaMemcpyDeviceToHost));
             for (size_t p = 0; p < b->n_frames; p++) results[b->order[p]] = dev[p];
         }
-        if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC)) {
+        if (!(ctx->flags & CLX_OPT_NO_VERIFY_CRC) && !b->device_crc) {
             std::vector<uint8_t> tmp;
             for (size_t i = 0; i < b->n_frames; i++) {
                 if (results[i].status != CLX_OK) continue;

@@ -170,6 +170,12 @@ int clx_decode_frames_to(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, cons
 /* Device-resident variant: upload once, decode many times (kernel-only timing), read back. */
 int clx_batch_create(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
                      size_t n_frames, size_t out_elems, clx_batch** out);
+/* The same with `bytes` in DEVICE memory of the context's GPU (CLX_BATCH_BYTES_ON_DEVICE): e.g. a shard that
+ * arrived over NVLink by the one NCCL scatter (claxon_b200/shard.py).  Nothing of it ever passes through the host:
+ * the frame CRC-16 is then checked on the device as part of every decode. */
+#define CLX_BATCH_BYTES_ON_DEVICE 1u
+int clx_batch_create_ex(clx_ctx* ctx, const uint8_t* bytes, size_t nbytes, const clx_frame_desc* descs,
+                        size_t n_frames, size_t out_elems, uint32_t batch_flags, clx_batch** out);
 int clx_batch_decode(clx_ctx* ctx, clx_batch* b, uint32_t stream_index); /* async on an internal stream */
 int clx_batch_sync(clx_ctx* ctx, clx_batch* b);
 int clx_batch_read(clx_ctx* ctx, clx_batch* b, int32_t* out, size_t out_elems, clx_frame_result* results);

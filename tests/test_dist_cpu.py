@@ -48,6 +48,15 @@ def _worker(rank, world, port, q):
             a = pcm[int(local[i]["out_offset"]):int(local[i]["out_offset"]) + n]
             e = whole[int(g["out_offset"]):int(g["out_offset"]) + n]
             ok &= bool(np.array_equal(a, e))
+        # the matching gather: rank 0 ends up with the whole batch's PCM
+        got = shard.gather_pcm(dist, torch.from_numpy(pcm[: o1 - o0].copy()), (o0, o1), out_elems, dst=0)
+        if rank == 0:
+            for g in descs:
+                n = int(g["n_channels"]) * int(g["block_size"])
+                o = int(g["out_offset"])
+                ok &= bool(np.array_equal(got.numpy()[o:o + n], whole[o:o + n]))
+        else:
+            ok &= got is None
         # gather of sample counts: totals must add up
         t = torch.tensor([int(sum(int(d["n_channels"]) * int(d["block_size"]) for d in local))])
         dist.all_reduce(t)

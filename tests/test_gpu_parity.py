@@ -481,3 +481,27 @@ def test_tightly_packed_odd_blocks_many_chunks(ctx):
     out, res = ctx.decode_frames(b.data, descs, out=out)
     assert (res["status"] == 0).all() and out[0] == 77 and out[-1] == 77
     assert np.array_equal(out[1:-1], b.pcm)
+
+
+def test_batch_from_device_bytes_checks_crc_on_device():
+    """clx_batch_create_ex(CLX_BATCH_BYTES_ON_DEVICE): the shard a rank received over NVLink never visits the host; its
+    frame CRC-16 is verified by the device kernel — statuses (incl. "frame CRC mismatch") as the oracle's."""
+    import torch
+    c = cb.Context(device=0)
+    b = synth.workload("c3", 200)
+    data = b.data.copy()
+    victims = [7, 150]
+    for v in victims:
+        data[int(b.frame_offsets[v]) + int(b.frame_lengths[v]) // 3] ^= 0x04
+    descs, out_elems = cb.descs_from_offsets(data, b.frame_offsets[:-1], b.frame_lengths)
+    t = torch.from_numpy(data).cuda()
+    dev = c.adopt(t.data_ptr(), t.numel(), descs, out_elems)
+    dev.decode(0)
+    out, res = dev.read()
+    bad, st, ref = O.decode_batch(data, b.frame_offsets[:-1], b.frame_lengths, descs["out_offset"], out_elems, n_threads=8)
+    assert np.array_equal(res["status"], st) and set(np.nonzero(st)[0].tolist()) == set(victims)
+    for i in np.nonzero(st == 0)[0]:
+        o, n = int(descs[i]["out_offset"]), int(descs[i]["n_channels"]) * int(descs[i]["block_size"])
+        assert np.array_equal(out[o:o + n], ref[o:o + n])
+    dev.close()
+    c.close()
