@@ -25,7 +25,7 @@ from ._lib import (FrameDesc, FrameResult, OPT_NO_VERIFY_CRC, OPT_GENERIC_KERNEL
                    OUT_PLANAR_I32, OUT_INTERLEAVED_I32, OUT_INTERLEAVED_I16, OUT_INTERLEAVED_I24)
 
 __all__ = ["Error", "Block", "FrameReader", "FlacReader", "FlacReaderOptions", "StreamInfo", "Context", "DeviceBatch",
-           "parse_frame_header", "demux_frames", "open_stream", "status_str", "DESC_DTYPE", "RESULT_DTYPE"]
+           "parse_frame_header", "demux_frames", "open_stream", "ogg_frames", "mp4_frames", "status_str", "DESC_DTYPE", "RESULT_DTYPE"]
 
 # numpy views of the C structs (same layout; asserted below)
 DESC_DTYPE = np.dtype([
@@ -136,6 +136,31 @@ def demux_frames(data, start: int = 0, max_frames: int = 1 << 20, flags: int = 0
         if n < cap or cap >= max_frames:
             return descs[:n].copy(), nxt.value, total.value, stop.value
         cap = min(max_frames, cap * 4)
+
+
+def ogg_frames(data, flags: int = 0):
+    """Frames of an in-memory Ogg FLAC file (examples/decode_ogg.rs): (StreamInfo, frame bytes, descs, out_elems);
+    the descriptors index the returned byte array (packets may span pages in the file)."""
+    buf = _as_u8(data)
+    si = _lib.StreamInfoC()
+    frames = np.zeros(max(16, buf.size), dtype=np.uint8)
+    descs = np.zeros(max(16, buf.size // 8), dtype=DESC_DTYPE)
+    n, used, total = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0)
+    _check(_lib.load().clx_ogg_frames(buf.ctypes.data, buf.size, C.byref(si), frames.ctypes.data, frames.size,
+                                      descs.ctypes.data, descs.size, C.byref(n), C.byref(used), C.byref(total), flags))
+    return StreamInfo._from_c(si), frames[: used.value].copy(), descs[: n.value].copy(), int(total.value)
+
+
+def mp4_frames(data, flags: int = 0):
+    """Frames of an in-memory MP4 file with a 'fLaC' track (examples/decode_mp4.rs): (StreamInfo, descs, out_elems);
+    the descriptors index `data` itself."""
+    buf = _as_u8(data)
+    si = _lib.StreamInfoC()
+    descs = np.zeros(max(16, buf.size // 8), dtype=DESC_DTYPE)
+    n, total = C.c_size_t(0), C.c_uint64(0)
+    _check(_lib.load().clx_mp4_frames(buf.ctypes.data, buf.size, C.byref(si), descs.ctypes.data, descs.size, C.byref(n),
+                                      C.byref(total), flags))
+    return StreamInfo._from_c(si), descs[: n.value].copy(), int(total.value)
 
 
 def descs_from_offsets(data, offsets, lengths=None, flags: int = 0) -> tuple[np.ndarray, int]:

@@ -130,6 +130,27 @@ size_t clx_demux_frames(const uint8_t* bytes, size_t n, uint64_t start, clx_fram
                         size_t max_frames, uint64_t* next_offset, uint64_t* total_out_elems,
                         int* stop_status, uint32_t flags);
 
+/* Container feeds: a wrapper that stores one FLAC frame per packet / sample hands over
+ * the frame boundaries, so no search (clx_demux_frames) is needed.  What the reference leaves to the `ogg`
+ * and `mp4parse` crates in examples/decode_ogg.rs:26-125 and examples/decode_mp4.rs:26-167.
+ *
+ * clx_ogg_frames: an in-memory Ogg file with the FLAC mapping (first packet: 0x7F "FLAC" version, number of
+ * header packets, "fLaC", STREAMINFO; then the header packets; then one frame per packet; empty packets
+ * skipped; page CRCs verified unless CLX_OPT_NO_VERIFY_CRC).  Packets may span pages, so the frames are
+ * copied back to back into `frames_out` (capacity frames_cap; the file's size always suffices) and the
+ * descriptors index THAT buffer; byte_len is exact.
+ * clx_mp4_frames: an in-memory MP4 / ISO BMFF file; the first track with a 'fLaC' sample entry.  STREAMINFO
+ * comes from its dfLa box, frame extents from stsz + stsc + stco/co64; samples are contiguous in the file, so
+ * the descriptors index the file's own bytes.
+ * Both fill out_offset back to back (4-element aligned) and return CLX_ERR_CONTAINER for a malformed wrapper,
+ * a frame-header status if a packet / sample is not a frame, CLX_ERR_INVALID_ARGUMENT if max_frames or
+ * frames_cap is too small. */
+int clx_ogg_frames(const uint8_t* ogg, size_t n, clx_streaminfo* si, uint8_t* frames_out, size_t frames_cap,
+                   clx_frame_desc* descs, size_t max_frames, size_t* n_frames, size_t* frames_bytes,
+                   uint64_t* total_out_elems, uint32_t flags);
+int clx_mp4_frames(const uint8_t* mp4, size_t n, clx_streaminfo* si, clx_frame_desc* descs, size_t max_frames,
+                   size_t* n_frames, uint64_t* total_out_elems, uint32_t flags);
+
 uint8_t clx_crc8(const uint8_t* p, size_t n);   /* src/crc.rs: poly 0x07, init 0 */
 uint16_t clx_crc16(const uint8_t* p, size_t n); /* src/crc.rs: poly 0x8005, init 0 */
 

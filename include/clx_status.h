@@ -81,7 +81,8 @@ typedef enum clx_status {
     /* --- library level (no claxon counterpart) --- */
     CLX_ERR_INVALID_ARGUMENT = 90,
     CLX_ERR_CUDA = 91,
-    CLX_ERR_NO_DEVICE = 92
+    CLX_ERR_NO_DEVICE = 92,
+    CLX_ERR_CONTAINER = 93      /* malformed / unsupported Ogg or MP4 wrapper (the reference leaves containers to other crates) */
 } clx_status;
 
 /* Error variant of a status, mirroring claxon::Error. */
@@ -146,6 +147,7 @@ static inline const char* clx_status_str_inline(int s) {
     case CLX_ERR_INVALID_ARGUMENT: return "claxon_b200: invalid argument";
     case CLX_ERR_CUDA: return "claxon_b200: CUDA error";
     case CLX_ERR_NO_DEVICE: return "claxon_b200: no CUDA device / extension not available";
+    case CLX_ERR_CONTAINER: return "claxon_b200: malformed or unsupported container";
     default: return "claxon_b200: unknown status";
     }
 }
@@ -157,7 +159,7 @@ static inline int clx_status_kind_inline(int s) {
     case CLX_ERR_NO_BPS_IN_HEADER: case CLX_ERR_UNENCODED_BINARY: case CLX_ERR_NEGATIVE_QLP_SHIFT:
     case CLX_ERR_VORBIS_TOO_LARGE: case CLX_ERR_APPLICATION_TOO_LARGE:
         return CLX_KIND_UNSUPPORTED;
-    case CLX_ERR_INVALID_ARGUMENT: case CLX_ERR_CUDA: case CLX_ERR_NO_DEVICE:
+    case CLX_ERR_INVALID_ARGUMENT: case CLX_ERR_CUDA: case CLX_ERR_NO_DEVICE: case CLX_ERR_CONTAINER:
         return CLX_KIND_LIBRARY;
     default:
         return (s >= 3 && s < 90) ? CLX_KIND_FORMAT : CLX_KIND_LIBRARY;

@@ -296,3 +296,50 @@ def test_open_stream_ex_stops_early(golden):
     assert e.value.status == 43            # "vendor string too long"
     r = cb.FlacReader.new_ext(data, cb.FlacReaderOptions(metadata_only=True, read_vorbis_comment=False))
     assert r.streaminfo().bits_per_sample == 16
+
+
+# --------------------------------------------------------------------------- container feeds
+
+def _check_container_descs(b, frame_bytes, descs, total, si):
+    from oracle import oracle as O
+    assert descs.size == b.n_frames and si.channels == b.config.n_channels and si.bits_per_sample == b.config.bps
+    assert np.array_equal(descs["byte_len"], b.frame_lengths)  # exact extents, straight from the container
+    bad, st, pcm = O.decode_batch(frame_bytes, descs["byte_offset"], descs["byte_len"], descs["out_offset"], total, n_threads=4)
+    assert bad == 0
+    for i in range(b.n_frames):
+        o = int(descs[i]["out_offset"]); lo, hi = int(b.pcm_offsets[i]), int(b.pcm_offsets[i + 1])
+        assert np.array_equal(pcm[o:o + hi - lo], b.pcm[lo:hi])
+
+
+def test_ogg_packets_become_frame_descriptors():
+    """examples/decode_ogg.rs: header packets skipped, one frame per packet, packets spanning pages reassembled, the
+    empty last packet and a foreign logical stream ignored, page CRCs verified."""
+    from tests import containers
+    b = synth.workload("c3", 9)      # ~12 KB frames: every one spans several pages of 40 segments
+    ogg = np.frombuffer(containers.flac_in_ogg(b), dtype=np.uint8)
+    si, frames, descs, total = cb.ogg_frames(ogg)
+    assert si.samples == b.n_samples // 2 and frames.size == b.data.size
+    _check_container_descs(b, frames, descs, total, si)
+    damaged = ogg.copy()
+    damaged[len(damaged) // 2] ^= 1    # a flipped payload bit: the page checksum catches it
+    with pytest.raises(cb.Error) as e:
+        cb.ogg_frames(damaged)
+    assert e.value.status == 93
+    assert cb.ogg_frames(damaged, flags=cb.OPT_NO_VERIFY_CRC)[2].size == 9  # ... unless told not to look
+    with pytest.raises(cb.Error):
+        cb.ogg_frames(b.data)          # not an Ogg file at all
+
+
+@pytest.mark.parametrize("co64", [False, True])
+def test_mp4_sample_tables_become_frame_descriptors(co64):
+    """examples/decode_mp4.rs: the first 'fLaC' track (another track comes first in the file), STREAMINFO from dfLa,
+    frame extents from stsz + stsc runs + stco / co64; the descriptors index the file itself."""
+    from tests import containers
+    b = synth.workload("c4", 22)
+    mp4 = np.frombuffer(containers.flac_in_mp4(b, co64=co64), dtype=np.uint8)
+    si, descs, total = cb.mp4_frames(mp4)
+    _check_container_descs(b, mp4, descs, total, si)
+    assert not np.array_equal(np.diff(descs["byte_offset"].astype(np.int64)), b.frame_lengths[:-1])  # chunks are apart
+    with pytest.raises(cb.Error) as e:
+        cb.mp4_frames(mp4[: mp4.size // 3])  # sample tables point past the end
+    assert e.value.status == 93
