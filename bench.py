@@ -521,9 +521,13 @@ def main():
         if not args.no_extra and args.workload == "c2" and args.scaling == "weak":
             job.close()
             extra = {}
-            for wl, nu in (("c3", 8), ("c4", 48), ("c5", 4)):  # ~65 000 frames in flight like c2 (c5: memory-bound choice)
+            # Mixed shapes keep fewer lanes of a warp busy, so these batches need more of them in flight than c2 to
+            # fill the chip (c4, 1100-frame units: 48 in flight 95, 96 -> 126, 128 -> 146 Gsamples/s,
+            # profiles/c4_units_in_flight_r02.txt); c5's frames are 128 times longer than their count suggests.
+            cx = cb.Context(device=local, n_streams=128, host_threads=host_threads)
+            for wl, nu in (("c3", 16), ("c4", 128), ("c5", 16)):
                 try:
-                    extra[wl] = short_line(cb, synth, ctx, wl, nu, min(args.streams, nu))
+                    extra[wl] = short_line(cb, synth, cx, wl, nu, min(128, nu))
                 except Exception as e:  # never lose the headline line to an auxiliary measurement
                     extra[wl] = {"error": f"{type(e).__name__}: {e}"}
 

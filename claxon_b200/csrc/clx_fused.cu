@@ -76,24 +76,37 @@ struct DeviceIO {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    // Before a read of at most 64 bytes from bitpos on (a header field, a single code, a window seat): nothing to
-    // do if the steady-state refill is far enough ahead — what lies that far behind its front has landed, by the
-    // wait of the last prefetch_group() — else a blocking refill.
+    // Before a read of at most 16 bytes from bitpos on (a header field, a single code, a window seat): nothing to
+    // do if the steady-state refill is far enough ahead — at most max(WAITN, 4) quads behind its front are still
+    // in flight, see prefetch_group() — else a blocking refill.
     __device__ __forceinline__ void ensure_near(uint32_t bitpos) {
-        if (fq < (bitpos >> 7) + 4u + WAITN) ensure(bitpos);
+        if (fq < (bitpos >> 7) + 2u + (WAITN > 4u ? WAITN : 4u)) ensure(bitpos);
     }
     // Steady state, once per group of eight codes.  A group consumes at most 256 bits = 2 quads (C2: 0.36 on
     // average): one predicated copy per group keeps the ring ahead of light streams, a second one — behind a
     // branch that light streams never take — keeps it ahead of dense ones (large Rice parameters: a quad per
-    // group and more).  The group needs quads up to (bitpos >> 7) + 3; copies of the last WAITN groups may
-    // still be in flight.  False: the ring is not far enough ahead (the caller refills it with ensure()).
+    // group and more).  The group needs quads up to (bitpos >> 7) + 3; copies of the last WAITN light groups may
+    // still be in flight.  Always true here (the host harness's policy shares the signature).
     __device__ __forceinline__ bool prefetch_group(uint32_t bitpos) {
         const uint32_t q0 = bitpos >> 7;
         if (fq < q0 + RQ) { issue(fq); fq++; }
-        while (fq < q0 + RQ) { issue(fq); fq++; }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group %0;" ::"n"(WAITN) : "memory");
-        return fq >= q0 + 4 + WAITN;
+        if (fq < q0 + RQ) {  // a dense stretch: a second quad this group (more than two only after a jump of the cursor)
+            issue(fq); fq++;
+            const bool more = fq < q0 + RQ;
+            while (fq < q0 + RQ) { issue(fq); fq++; }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // A group of two quads waits for everything older, so that the copies in flight never exceed four
+            // quads (this pair plus at most one from each of two later light groups): the RQ - 4 quads from the
+            // cursor on, which is what a group reads, have always landed.
+            // (A ring with room for two quads from each of WAITN groups beyond the four being read needs none of this.)
+            if (more) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            else if (2u * WAITN + 4u <= RQ) asm volatile("cp.async.wait_group %0;" ::"n"(WAITN) : "memory");
+            else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(WAITN) : "memory");
+        }
+        return true;
     }
     __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t lane, const uint8_t* bytes, uint64_t buf_bytes,
                                          uint64_t byte_offset) {
@@ -105,6 +118,7 @@ struct DeviceIO {
         gbase = reinterpret_cast<const uint4*>(bytes + aligned);
         qlim = (uint32_t)min((buf_bytes - aligned) >> 4, (uint64_t)0x1ffffffu);
     }
+    __device__ __forceinline__ void close() { asm volatile("cp.async.wait_all;" ::: "memory"); }
     __device__ __forceinline__ void open_idle(uint32_t ring_addr, uint32_t lane, const uint8_t* bytes) {
         ring = ring_addr;
         rot = (lane & 7u) << 4;
@@ -115,30 +129,149 @@ struct DeviceIO {
     }
 };
 
+
+// ---------------------------------------------------------------------------------
+// Device IO policy of a lane, TMA flavour: a ring of two CHUNK-byte halves in shared memory, each filled by
+// one bulk copy (`cp.async.bulk`, SASS UBLKCP) that signals the half's own mbarrier
+// ---------------------------------------------------------------------------------
+// Chunk c of the frame (CHUNK bytes from its 16-byte aligned base) lives in half c & 1.  A half is re-armed
+// only after the cursor has left the chunk it held, so at most one copy per half is ever outstanding and the
+// parity to wait for simply alternates.  Reads past the end of the byte buffer see the buffer's last chunk
+// instead (never a fault); running past a frame's own bytes is detected by position, as everywhere.
+template <uint32_t CHUNK>
+struct TmaIO {
+    static constexpr uint32_t BYTES = 2 * CHUNK;
+    static constexpr uint32_t CB = CHUNK * 8;     // bits per chunk
+    static constexpr uint32_t LANE_BYTES = BYTES + 16;  // ring + two mbarriers; 16 bytes of bank skew between lanes
+    uint32_t ring;         // shared-space address of the lane's ring (16-byte aligned); the mbarriers follow it
+    const uint8_t* gbase;  // the frame's 16-byte aligned base
+    uint32_t clim;         // highest chunk index that lies inside the byte buffer
+    uint32_t creq;         // chunks below creq have been requested (the ring holds creq - 2 and creq - 1)
+    uint32_t cready;       // chunks below cready have landed
+    uint32_t phase;        // bit h: the parity half h's mbarrier completes next
+    uint32_t wp;           // byte offset (unmasked) of the next word of the register window
+    bool live;
+
+    __device__ __forceinline__ void request(uint32_t c) {
+        const uint32_t h = c & 1u;
+        const uint32_t bar = ring + BYTES + h * 8u, dst = ring + h * CHUNK;
+        const uint8_t* src = gbase + (size_t)min(c, clim) * CHUNK;
+        // order this thread's earlier generic-proxy reads of the half before the async-proxy write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(CHUNK) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "n"(CHUNK), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ void wait(uint32_t c) {
+        const uint32_t h = c & 1u;
+        const uint32_t bar = ring + BYTES + h * 8u, parity = (phase >> h) & 1u;
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        } while (!done);
+        phase ^= 1u << h;
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t wi) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + ((wi << 2) & (BYTES - 4u))) : "memory");
+        return __byte_perm(v, 0, 0x0123);
+    }
+    __device__ __forceinline__ void seek_next(uint32_t wi) { wp = wi << 2; }
+    __device__ __forceinline__ uint32_t next_raw() {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (wp & (BYTES - 4u))) : "memory");
+        wp += 4;
+        return v;
+    }
+    // Random access (headers, slow codes): on return the chunk of bitpos has landed, and the next one too if
+    // bitpos is within 32 bytes of it (no caller reads further than that without asking again).
+    __device__ __forceinline__ void ensure(uint32_t bitpos) {
+        if (!live) return;
+        const uint32_t c0 = bitpos / CB, c1 = (bitpos + 256u) / CB;
+        if (creq < c0) {  // the cursor jumped past everything requested: drain, then start over at its chunk
+            while (cready < creq) { wait(cready); cready++; }
+            creq = cready = c0;
+        }
+        while (creq < c0 + 2u) { request(creq); creq++; }
+        while (cready <= c1) { wait(cready); cready++; }
+    }
+    __device__ __forceinline__ void ensure_near(uint32_t bitpos) {
+        if (creq < bitpos / CB + 2u || cready <= (bitpos + 256u) / CB) ensure(bitpos);
+    }
+    // Steady state, once per group of eight codes (at most 256 bits, plus the window's three words of look-ahead).
+    __device__ __forceinline__ bool prefetch_group(uint32_t bitpos) {
+        const uint32_t c0 = bitpos / CB, c1 = (bitpos + 384u) / CB;
+        if (live && creq < c0 + 2u) {
+            if (creq < c0 + 1u) ensure(bitpos);  // (after a jump of the cursor)
+            else { request(creq); creq++; }      // the cursor has just left chunk c0 - 1: its half takes chunk c0 + 1
+        }
+        while (live && cready <= c1) { wait(cready); cready++; }
+        return true;
+    }
+    // No copy into this CTA's shared memory may be in flight when the CTA retires.
+    __device__ __forceinline__ void close() {
+        while (cready < creq) { wait(cready); cready++; }
+    }
+    __device__ __forceinline__ void open_idle(uint32_t ring_addr, uint32_t, const uint8_t* bytes) {
+        ring = ring_addr;
+        gbase = bytes;
+        clim = 0; creq = 0; cready = 0; phase = 0; wp = 0;
+        live = false;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring + BYTES) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring + BYTES + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // (after open_idle(), which initialised the lane's mbarriers)
+    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t, const uint8_t* bytes, uint64_t buf_bytes, uint64_t byte_offset) {
+        ring = ring_addr;
+        const uint64_t aligned = byte_offset & ~15ull;
+        gbase = bytes + aligned;
+        const uint64_t chunks = (buf_bytes - aligned) / CHUNK;  // the buffer is padded: at least one
+        clim = (uint32_t)min(chunks - 1, (uint64_t)0x3fffffu);
+        creq = 0; cready = 0; wp = 0;
+        live = true;
+    }
+};
+
 // ---------------------------------------------------------------------------------
 // Kernel 1: index pass, one lane per frame
 // ---------------------------------------------------------------------------------
 constexpr uint32_t IDX_RQ = 16;
+#ifdef CLX_RING_TMA
+using IndexIO = TmaIO<128>;
+#else
 using IndexIO = DeviceIO<IDX_RQ, 6>;
+#endif
 
 __global__ void __launch_bounds__(32)
 index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const clx_frame_desc* __restrict__ descs,
                     uint32_t n_frames, clx_frame_result* __restrict__ results, SeqParams* __restrict__ params, uint32_t CH,
                     int* __restrict__ need_generic) {
+#ifdef CLX_RING_TMA
+    __shared__ __align__(16) uint8_t s_ring[32][IndexIO::LANE_BYTES];
+#else
     __shared__ __align__(256) uint4 s_ring[32][IDX_RQ];
+#endif
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t fidx = blockIdx.x * 32 + lane;
     const bool live = fidx < n_frames;
 
     IndexLane<IndexIO> L;
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&s_ring[lane][0]);
+    L.rc.io.open_idle(ring, lane, bytes);
     if (live) {
         const clx_frame_desc d = descs[fidx];
         L.rc.io.open(ring, lane, bytes, buf_bytes, d.byte_offset);
         L.init(d, params + (size_t)fidx * CH, CH);
     } else {
         clx_frame_desc d = {};
-        L.rc.io.open_idle(ring, lane, bytes);
         L.init(d, params, CH);
         L.mode = SEQ_DONE;
         L.rc.ok = true;
@@ -151,6 +284,7 @@ index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const
         else if (!L.done()) L.slow_step();
         __syncwarp();
     }
+    L.rc.io.close();
     if (live) {
         clx_frame_result res;
         res.status = L.ok() ? (int32_t)CLX_OK : (int32_t)CLX_INTERNAL_NEED_GENERIC;
@@ -165,7 +299,11 @@ index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const
 // ---------------------------------------------------------------------------------
 constexpr int DEC_WARPS = 2;
 constexpr uint32_t DEC_RQ = 8;
+#ifdef CLX_RING_TMA
+using SubIO = TmaIO<64>;
+#else
 using SubIO = DeviceIO<DEC_RQ, 3>;
+#endif
 
 // One trip of the recurrence for U consecutive samples.  v[0..TAPS) = history (oldest first),
 // v[TAPS+i] = sample i of this trip.  Terms that only involve history are summed first, the terms
@@ -315,7 +453,7 @@ __device__ __forceinline__ void flush_quarter_fast(uint32_t tile_s, uint32_t out
 template <int TAPS, int U, typename ACC, int FMODE>
 __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint32_t order, uint32_t shift,
                                             const SeqParams* __restrict__ sp, bool active, int32_t* tile, uint32_t tile_s,
-                                            const SeqRow* pr, uint32_t outp_s, int32_t* slow_e, uint32_t lane, bool all_vec,
+                                            const SeqRow* pr, uint32_t outp_s, uint32_t lane, bool all_vec,
                                             bool any_wasted, int32_t& smin, int32_t& smax) {
     int32_t c[TAPS], h[TAPS];  // c[j] multiplies s[t-1-j]; h[j] = s[t-1-j]
 #pragma unroll
@@ -387,6 +525,8 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
                 if (L.fast()) got = L.fast_group(dst);
             }
             if (!got) {  // a partition boundary inside the group, a code longer than the window, verbatim ...
+                int32_t slow_e[8];  // indexed by a loop variable on purpose: local memory, touched on this slow path only
+#pragma unroll 1
                 for (int i = 0; i < 8; i++) slow_e[i] = L.next();
 #pragma unroll
                 for (int i = 0; i < 8; i++) dst[i] = slow_e[i];
@@ -428,19 +568,41 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
         };
         // MP: some subframe of the warp has a partition boundary ahead (its own instance of the loop, so that warps
         // of single-partition subframes do not even look)
+        // COMPACT: the bodies that warps of mixed batches end up in (general flush: irregular rows, or the i64
+        // accumulator).  An SM then runs several DIFFERENT bodies at once and its 32 KB instruction cache holds
+        // the loops of all of them only if each is small: one trip per iteration (the residuals are copied
+        // instead of alternating between two register sets), one code per window refill, one instance for
+        // single- and multi-partition warps.  The regular bodies (FMODE != 0: whole batches of one shape, one
+        // loop on every SM) keep the unrolled, specialised form.
+        constexpr bool COMPACT = FMODE == 0;
+        uint32_t nc_fixed = 1;
         auto step = [&](auto mp, const int32_t (&cons)[8], int32_t (&prod)[8], uint32_t t) {
             if (decltype(mp)::value && active && !L.fast()) L.quick_prepare();  // a partition header, from the window
-            // codes per window refill: what every lane on the fast path allows (by its partition's Rice parameter)
-            const uint32_t nc = __reduce_min_sync(0xffffffffu, L.spec_cap());
             bool good;
-            if (nc == 2) { good = L.template spec_group<2>(prod); consume(cons, t); }
-            else { good = L.template spec_group<1>(prod); consume(cons, t); }
+            if (COMPACT) { good = L.template spec_group<1>(prod); consume(cons, t); }
+            else {
+                // codes per window refill: what every lane on the fast path allows (by its partition's Rice parameter);
+                // fixed for the whole loop when no lane has a partition boundary ahead
+                const uint32_t nc = decltype(mp)::value ? __reduce_min_sync(0xffffffffu, L.spec_cap()) : nc_fixed;
+                if (nc == 2) { good = L.template spec_group<2>(prod); consume(cons, t); }
+                else { good = L.template spec_group<1>(prod); consume(cons, t); }
+            }
             if (!good && active) produce(prod, true);  // rare
             after(t);
         };
         if (active) produce(rA, true);
         uint32_t t = head_end;
         auto run = [&](auto mp) {
+            if (COMPACT) {
+                while (t + 8 < bulk_end) {
+                    step(mp, rA, rB, t);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) rA[i] = rB[i];
+                    t += 8;
+                }
+                consume(rA, t);
+                return;
+            }
             while (t + 16 < bulk_end) {
                 step(mp, rA, rB, t);
                 step(mp, rB, rA, t + 8);
@@ -452,8 +614,11 @@ __device__ __forceinline__ void decode_rows(SubLane<SubIO>& L, uint32_t bs, uint
                 consume(rB, t);
             } else consume(rA, t);
         };
-        if (__any_sync(0xffffffffu, active && L.rc.parts_left != 0)) run(std::true_type{});
-        else run(std::false_type{});
+        if (COMPACT || __any_sync(0xffffffffu, active && L.rc.parts_left != 0)) run(std::true_type{});
+        else {
+            nc_fixed = __reduce_min_sync(0xffffffffu, active ? L.last_cap() : 2u);
+            run(std::false_type{});
+        }
         after(t);
         if (have_drain) {  // whatever of the last full tile has not been written yet (re-writing a quarter is harmless)
             const uint32_t g0 = (bulk_end & ~31u) - 32;
@@ -485,8 +650,11 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     __shared__ __align__(8192) int32_t s_tile[DEC_WARPS][2 * 32 * 32];  // two tiles: one fills while the other drains
     __shared__ SeqRow s_rows[DEC_WARPS][32];
     __shared__ __align__(16) int32_t* s_outp[DEC_WARPS][32];
+#ifdef CLX_RING_TMA
+    __shared__ __align__(16) uint8_t s_ring[DEC_WARPS][32][SubIO::LANE_BYTES];
+#else
     __shared__ __align__(128) uint4 s_ring[DEC_WARPS][32][DEC_RQ];
-    __shared__ int32_t s_slow[DEC_WARPS][32][8];
+#endif
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t pw = blockIdx.x * DEC_WARPS + warp;  // CH subframe warps per group of 32 frames
     if (pw >= n_pwarps) return;
@@ -555,7 +723,7 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     int32_t smin = 0, smax = 0;
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t outp_s = (uint32_t)__cvta_generic_to_shared(&s_outp[warp][0]);
-#define CLX_ROWS(T, UU, A, F) decode_rows<T, UU, A, F>(L, bs, order, shift, sp, active, tile, tile_s, pr, outp_s, s_slow[warp][lane], lane, all_vec, any_wasted, smin, smax)
+#define CLX_ROWS(T, UU, A, F) decode_rows<T, UU, A, F>(L, bs, order, shift, sp, active, tile, tile_s, pr, outp_s, lane, all_vec, any_wasted, smin, smax)
     // straight-line flush variants only where they pay: the i32-accumulator bodies (16-bit audio)
 #define CLX_BODY(T, UU)                                    \
     do {                                                   \
@@ -586,6 +754,7 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     // The subframe must end inside the frame; the lane of the last subframe locates the CRC-16 footer
     // (pad bits up to the byte boundary are skipped unchecked, src/frame.rs:744-754).
     const uint32_t end_bit = L.finish();
+    L.rc.io.close();
     bool redo = !L.ok();
     if (last && !redo) {
         const uint32_t consumed = ((end_bit - bit0 + 7) >> 3) + 2;

@@ -113,7 +113,7 @@ enum : uint32_t { SEQ_SUBFRAME = 0, SEQ_PART = 1, SEQ_RUN = 2, SEQ_DONE = 3 };
 //   void ensure(uint32_t bitpos)          the bits from bitpos on (ring size minus slack) are readable through word()
 //   bool prefetch_group(uint32_t bitpos)  steady-state refill, once per fast group; false: ensure() before reading on
 //   void seek_next(uint32_t wi), uint32_t next_raw()   sequential word reads, bytes as stored (the register window's refill)
-//   void ensure_near(uint32_t bitpos)     cheap: the next 64 bytes from bitpos are readable (refills, blocking, only if not)
+//   void ensure_near(uint32_t bitpos)     cheap: the next 16 bytes from bitpos are readable (refills, blocking, only if not)
 
 // ---------------------------------------------------------------------------------
 // Bit window + Rice partition state shared by both lanes
@@ -555,6 +555,8 @@ struct SubLane {
     CLX_HD bool fast_group(int32_t (&e)[8]) { return rc.fast_group(e); }
     // codes per refill spec_group may use for this lane (a lane off the fast path does not care)
     CLX_HD uint32_t spec_cap() const { return rc.n_fast == 0 ? 2u : rc.ncap; }
+    // the same for the rest of the subframe, once its last partition has begun (parts_left == 0)
+    CLX_HD uint32_t last_cap() const { return kind == SUB_PREDICTED && rc.ok ? rc.ncap : 2u; }
     template <int NC>
     CLX_HD bool spec_group(int32_t (&e)[8]) { return rc.template spec_group<NC>(e); }
     // one residual through the slow path, whatever the subframe's kind; 0 once the lane has failed

@@ -1,4 +1,5 @@
-"""Decodes one device-resident batch a few times (target for ncu): python tools/profile_batch.py <workload> <frames> <reps>."""
+"""Decodes one device-resident batch a few times (target for ncu): python tools/profile_batch.py <workload> <frames> <reps> [lane].
+`lane`: force the lane-per-frame throughput path (frames with very long index walks default to the warp-per-frame path)."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -9,7 +10,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else None
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 b = synth.workload(name, n)
-ctx = cb.Context()
+ctx = cb.Context(lane_per_frame=len(sys.argv) > 4 and sys.argv[4] == 'lane')
 descs, out_elems = cb.descs_from_offsets(b.data, b.frame_offsets[:-1], b.frame_lengths)
 dev = ctx.upload(b.data, descs, out_elems)
 for i in range(reps):
