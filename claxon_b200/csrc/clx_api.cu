@@ -271,6 +271,7 @@ int clx_ctx_create(const clx_options* opts, clx_ctx** out) {
     ctx->flags = opts ? opts->flags : 0;
     if (ctx->device < 0 || ctx->device >= count) { delete ctx; return CLX_ERR_NO_DEVICE; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) { delete ctx; return CLX_ERR_NO_DEVICE; }
+    if (clx::crc16_init() != cudaSuccess) { delete ctx; return CLX_ERR_CUDA; }
     uint32_t ns = opts && opts->n_streams ? opts->n_streams : 2;
     ns = std::min<uint32_t>(ns, 128);
     ctx->streams.resize(ns);

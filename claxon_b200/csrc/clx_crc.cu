@@ -39,23 +39,35 @@ static CrcPowers host_powers() {
     return t;
 }
 
+// Slicing-by-4 tables, built once on the host: t[k][b] = CRC of byte b followed by k zero bytes.
+struct CrcTables { uint16_t t[4][256]; };
+__device__ CrcTables g_crc_tables;
+
+static CrcTables host_tables() {
+    CrcTables T;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t d = i << 8;
+        for (int k = 0; k < 8; k++) d = (d & 0x8000u) ? ((d << 1) ^ 0x8005u) & 0xffffu : (d << 1) & 0xffffu;
+        T.t[0][i] = (uint16_t)d;
+    }
+    for (int k = 1; k < 4; k++)
+        for (uint32_t i = 0; i < 256; i++) {
+            const uint32_t v = T.t[k - 1][i];
+            T.t[k][i] = (uint16_t)(((v << 8) & 0xffffu) ^ T.t[0][v >> 8]);
+        }
+    return T;
+}
+
 __global__ void __launch_bounds__(CRC_WARPS * 32)
 crc16_frames_kernel(const uint8_t* __restrict__ bytes, const clx_frame_desc* __restrict__ descs, uint32_t n_frames,
                     clx_frame_result* __restrict__ results, CrcPowers pw) {
-    __shared__ uint16_t s_t[4][256];  // slicing-by-4 tables: s_t[k][b] = crc of byte b followed by k zero bytes
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t d = i << 8;
-        for (int k = 0; k < 8; k++) d = (d & 0x8000u) ? ((d << 1) ^ 0x8005u) & 0xffffu : (d << 1) & 0xffffu;
-        s_t[0][i] = (uint16_t)d;
+    __shared__ uint16_t s_t[4][256];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_crc_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_t[0][0]);
+        for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    for (int k = 1; k < 4; k++) {
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-            const uint32_t v = s_t[k - 1][i];
-            s_t[k][i] = (uint16_t)(((v << 8) & 0xffffu) ^ s_t[0][v >> 8]);
-        }
-        __syncthreads();
-    }
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * CRC_WARPS + (threadIdx.x >> 5);
     if (f >= n_frames) return;
@@ -76,13 +88,25 @@ crc16_frames_kernel(const uint8_t* __restrict__ bytes, const clx_frame_desc* __r
     const uint32_t vlo = lane * C, vhi = vlo + C;
     uint32_t a = vlo > pad ? vlo - pad : 0u, b = vhi > pad ? vhi - pad : 0u;
     uint32_t crc = 0;
-    // head up to a 4-byte aligned address, whole words, tail
-    while (a < b && ((uintptr_t)(p + a) & 3u)) { crc = ((crc << 8) & 0xffffu) ^ s_t[0][(crc >> 8) ^ p[a]]; a++; }
-    for (; a + 4 <= b; a += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(p + a);  // little-endian: first byte in bits 0-7
+    auto byte_step = [&](uint32_t x) { crc = ((crc << 8) & 0xffffu) ^ s_t[0][(crc >> 8) ^ x]; };
+    // little-endian word: first byte in bits 0-7.  Only two of the four lookups depend on the running value.
+    auto word_step = [&](uint32_t w) {
         crc = s_t[3][((crc >> 8) ^ w) & 0xffu] ^ s_t[2][((crc ^ (w >> 8)) & 0xffu)] ^ s_t[1][(w >> 16) & 0xffu] ^ s_t[0][w >> 24];
+    };
+    // head up to a 16-byte aligned address; 16-byte vectors, each loaded one iteration before it is used (the
+    // addresses do not depend on the running value, so the loads overlap the table chain); tail
+    while (a < b && ((uintptr_t)(p + a) & 15u)) { byte_step(p[a]); a++; }
+    if (a + 16 <= b) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p + a));
+        for (; a + 32 <= b; a += 16) {
+            const uint4 nx = __ldg(reinterpret_cast<const uint4*>(p + a + 16));
+            word_step(v.x); word_step(v.y); word_step(v.z); word_step(v.w);
+            v = nx;
+        }
+        word_step(v.x); word_step(v.y); word_step(v.z); word_step(v.w);
+        a += 16;
     }
-    while (a < b) { crc = ((crc << 8) & 0xffffu) ^ s_t[0][(crc >> 8) ^ p[a]]; a++; }
+    while (a < b) { byte_step(p[a]); a++; }
     // combine: after level j a lane holds the CRC of 2^(j+1) chunks (valid in lanes whose low j+1 bits are all ones)
 #pragma unroll
     for (int j = 0; j < 5; j++) {
@@ -93,6 +117,13 @@ crc16_frames_kernel(const uint8_t* __restrict__ bytes, const clx_frame_desc* __r
         const uint32_t stored = ((uint32_t)p[n] << 8) | p[n + 1];
         if (crc != stored) results[f].status = CLX_ERR_FRAME_CRC_MISMATCH;
     }
+}
+
+// Uploads the tables to the CURRENT device (a __device__ symbol has one instance per device); called once per
+// context from clx_ctx_create, never from inside a stream capture.
+cudaError_t crc16_init() {
+    static const CrcTables T = host_tables();
+    return cudaMemcpyToSymbol(g_crc_tables, &T, sizeof T);
 }
 
 cudaError_t launch_crc16(const uint8_t* d_bytes, const clx_frame_desc* d_descs, uint32_t n_frames, clx_frame_result* d_results,

@@ -724,14 +724,14 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t outp_s = (uint32_t)__cvta_generic_to_shared(&s_outp[warp][0]);
 #define CLX_ROWS(T, UU, A, F) decode_rows<T, UU, A, F>(L, bs, order, shift, sp, active, tile, tile_s, pr, outp_s, lane, all_vec, any_wasted, smin, smax)
-    // straight-line flush variants only where they pay: the i32-accumulator bodies (16-bit audio)
-#define CLX_BODY(T, UU)                                    \
-    do {                                                   \
-        if (!WIDE && narrow) {                             \
-            if (fmode == 2) CLX_ROWS(T, UU, int, 2);       \
-            else if (fmode == 1) CLX_ROWS(T, UU, int, 1);  \
-            else CLX_ROWS(T, UU, int, 0);                  \
-        } else CLX_ROWS(T, UU, long long, 0);              \
+    // straight-line flush variants only where they pay: the i32-accumulator bodies (16-bit audio).  The i64 bodies are
+    // what mixed batches run, several per SM at a time; there one body (12 taps, also for warps that would do with
+    // 8) beats two that evict each other from the instruction cache.
+#define CLX_INT(T, UU)                                 \
+    do {                                               \
+        if (fmode == 2) CLX_ROWS(T, UU, int, 2);       \
+        else if (fmode == 1) CLX_ROWS(T, UU, int, 1);  \
+        else CLX_ROWS(T, UU, int, 0);                  \
     } while (0)
     // The i32 accumulator is exact only while sum|coef| * max|sample| < 2^31, which is checked against the samples
     // actually produced.  Streams that keep to their nominal sample width never fail it; a frame whose samples do
@@ -745,10 +745,13 @@ decode_subframes_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, c
         L.rc.io.open(ring, lane, bytes, buf_bytes, descs[f].byte_offset);
         L.init(*sp, bs, bit0 + byte_len * 8);
     }
-    if (GROUP == 1) CLX_BODY(32, 4);
-    else if (cls == 0) CLX_BODY(8, 8);
-    else CLX_BODY(12, 4);
-#undef CLX_BODY
+    if (GROUP == 1) {
+        if (narrow) CLX_INT(32, 4);
+        else CLX_ROWS(32, 4, long long, 0);
+    } else if (!narrow) CLX_ROWS(12, 4, long long, 0);  // ONE call site, hence one copy of the body, for both order classes
+    else if (cls == 0) CLX_INT(8, 8);
+    else CLX_INT(12, 4);
+#undef CLX_INT
 #undef CLX_ROWS
     if (!active) return;
     // The subframe must end inside the frame; the lane of the last subframe locates the CRC-16 footer

@@ -43,6 +43,7 @@ cudaError_t launch_decode(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_
                           uint32_t n_frames, int32_t* d_out, clx_frame_result* d_results, int* d_flags,
                           void* d_params, const CoopPlan& plan, cudaStream_t stream, uint64_t* launches);
 // clx_crc.cu: frame CRC-16 of every frame that decoded (over the length the decode found), on the device
+cudaError_t crc16_init();  // once per context, on its device
 cudaError_t launch_crc16(const uint8_t* d_bytes, const clx_frame_desc* d_descs, uint32_t n_frames, clx_frame_result* d_results,
                          cudaStream_t stream);
 // clx_output.cu: planar i32 -> interleaved little-endian samples (CLX_OUT_* modes), frame by frame

@@ -383,7 +383,15 @@ struct IndexLane {
     CLX_HD bool fast_ready() const { return mode == SEQ_RUN && rc.n_fast != 0; }
     CLX_HD void fast_group() {
         if (!rc.skip_group()) { slow_budget = 8; return; }
-        if (rc.n_left == 0 && rc.parts_left == 0 && rc.ok) end_of_body();
+        if (rc.n_left == 0 && rc.ok) {
+            if (rc.parts_left == 0) end_of_body();
+            else if (rc.wvalid) {
+                // The next partition's parameter straight from the seated window, so that a warp whose lanes cross
+                // partition boundaries all the time (partitions of 32 codes: every fourth group) stays in its tight loop.
+                rc.quick_part();
+                if (!rc.ok) fail();
+            }
+        }
     }
     CLX_HD void end_of_body() {
         if (rc.o > rc.limit) { fail(); return; }
