@@ -356,13 +356,25 @@ def main():
 
     dist = None
     if world > 1:
-        # NCCL prints its version banner on stdout at some debug levels; this script's stdout is one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on STDOUT when a communicator comes up (NCCL_DEBUG=VERSION and above, which
+        # some launchers set); this script's stdout is one JSON line, so file descriptor 1 points at stderr until the
+        # first collective has run.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=f"cuda:{local}")
+            dist_mod.all_reduce(warm)
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         dist = dist_mod
 
     def barrier():
