@@ -114,6 +114,51 @@ def test_frame_header_parse_matches_oracle_on_mutations():
     assert n_ok > 50
 
 
+def _check_against_spec(buf, st_c, d, st_o=None, h=None):
+    """Product (and oracle) against the plain-Python statement of the reference in tests/spec_header.py."""
+    from tests import spec_header as S
+    kind, val = S.parse(bytes(buf))
+    if kind == "eof":
+        assert st_c == 1 and (st_o is None or st_o == 1)
+    elif kind == "err":
+        want = "UnexpectedEof" if val == S.EOF_MSG else val
+        assert cb.status_str(st_c) == want, (bytes(buf).hex(), cb.status_str(st_c), want)
+        assert st_o is None or st_o == st_c
+    else:
+        assert st_c == 0, (bytes(buf).hex(), cb.status_str(st_c))
+        want = (val["block_size"], val["sample_rate"], val["n_channels"], val["channel_assignment"],
+                val["bits_per_sample"], val["variable"], val["number"], val["header_len"])
+        assert _hdr_tuple_cb(d) == want, (bytes(buf).hex(), _hdr_tuple_cb(d), want)
+        if h is not None:
+            assert _hdr_tuple_o(h) == want
+
+
+def test_frame_header_parse_matches_independent_spec_on_mutations():
+    """The C++ parser and the C oracle share an author; tests/spec_header.py is a third statement of
+    src/frame.rs:131-316 (bitwise CRC-8, the reference's own control flow and error strings) that both must match."""
+    b = synth.generate(synth.SynthConfig(n_frames=6, block_size=1000, n_channels=2, stereo_mode=-1, force_bs16=1,
+                                         variable_blocking=1))
+    L = _lib.load()
+    rng = np.random.default_rng(11)
+    base = b.data[:16].copy()
+    kinds = set()
+    for trial in range(3000):
+        buf = base.copy()
+        for _ in range(rng.integers(0, 3)):
+            buf[rng.integers(0, 12)] = rng.integers(0, 256)
+        if trial % 3 == 0:  # a mutated header whose CRC-8 is right again: the field checks decide, not the checksum
+            st0, d0 = cb.parse_frame_header(buf.copy(), flags=cb.OPT_NO_VERIFY_CRC if hasattr(cb, "OPT_NO_VERIFY_CRC") else 1)
+            if st0 == 0:
+                buf[d0.header_len - 1] = L.clx_crc8(buf[: d0.header_len - 1].tobytes(), d0.header_len - 1)
+        n = int(rng.integers(0, 17))
+        cut = buf[:n].copy() if n else np.zeros(0, np.uint8)
+        st_o, h = O.read_frame_header(cut)
+        st_c, d = cb.parse_frame_header(cut)
+        _check_against_spec(cut, st_c, d, st_o, h)
+        kinds.add(st_c)
+    assert len(kinds) >= 6  # ok, eof, unexpected eof and several distinct format errors were all exercised
+
+
 def test_frame_header_all_codes():
     # every block-size / sample-rate / channel / bps code, CRC fixed up so only the codes decide
     L = _lib.load()
@@ -131,6 +176,7 @@ def test_frame_header_all_codes():
                 assert st_o == st_c, (bs_code, sr_code, cb_byte)
                 if st_o == 0:
                     assert _hdr_tuple_cb(d) == _hdr_tuple_o(h)
+                _check_against_spec(bytes(hdr), st_c, d)
             if sr_code > 1 and bs_code > 1:
                 break  # the full cross product is only needed for a couple of rows
 
@@ -296,6 +342,62 @@ def test_open_stream_ex_stops_early(golden):
     assert e.value.status == 43            # "vendor string too long"
     r = cb.FlacReader.new_ext(data, cb.FlacReaderOptions(metadata_only=True, read_vorbis_comment=False))
     assert r.streaminfo().bits_per_sample == 16
+
+
+def test_open_stream_matches_independent_spec_on_mutations(golden):
+    """Stream open (magic, metadata block walk, STREAMINFO checks, VORBIS_COMMENT validation, tags) of the product AND
+    of the oracle against tests/spec_metadata.py — a third statement of src/lib.rs:186-307 and
+    src/metadata.rs:212-545 — on the reference fixtures, a synthetic file, and thousands of byte mutations and
+    truncations of their metadata: same claxon error string, or same first frame offset / stream info / vendor / tags."""
+    from tests import spec_metadata as M
+    seeds = [golden[f"{n}__bytes"] for n in ("pop", "short", "wasted_bits", "empty_vorbis_comment",
+                                            "repeated_vorbis_comment", "non_subset")]
+    b = synth.workload("c4", 22)
+    seeds.append(np.frombuffer(synth.make_file(b, 0, 11, padding=64), np.uint8))
+    rng = np.random.default_rng(23)
+    seen = set()
+
+    def check(buf):
+        kind, val = M.open_stream(buf.tobytes())
+        try:
+            si, first = cb.open_stream(buf)
+            got = None
+        except cb.Error as e:
+            got = e.message
+        st_o = O.open_stream(buf)[0]
+        if kind == "err":
+            want = "UnexpectedEof" if val == M.EOF_MSG else val
+            assert got == want, (got, want)
+            assert cb.status_str(st_o) == want
+            seen.add(want)
+            return
+        assert got is None and st_o == 0, (got, st_o)
+        assert first == val["first_frame"]
+        assert (si.min_block_size, si.max_block_size, si.sample_rate, si.channels, si.bits_per_sample) == (
+            val["min_block_size"], val["max_block_size"], val["sample_rate"], val["channels"], val["bits_per_sample"])
+        assert (si.samples or 0) == val["samples"] and si.md5sum == val["md5sum"]
+        assert (si.min_frame_size or 0) == val["min_frame_size"] and (si.max_frame_size or 0) == val["max_frame_size"]
+        r = cb.FlacReader.new_ext(buf, cb.FlacReaderOptions(metadata_only=True))
+        assert r.vendor() == val["vendor"]
+        assert r.tags() == [(c[:i], c[i + 1:]) for c, i in val["comments"]]
+        seen.add("ok")
+
+    for seed in seeds:
+        seed = np.asarray(seed, dtype=np.uint8)
+        kind, val = M.open_stream(seed.tobytes())
+        assert kind == "ok"
+        meta_end = val["first_frame"]
+        check(seed)
+        for trial in range(400):
+            buf = seed[: meta_end + 64].copy()
+            for _ in range(int(rng.integers(1, 4))):
+                at = int(rng.integers(0, meta_end))
+                # bias towards the bytes that steer the walk: small values, high bits, '=' and friends
+                buf[at] = rng.choice([0, 1, 4, 0x7F, 0x80, 0x84, 0xFF, 0x3D, int(rng.integers(0, 256))])
+            if trial % 4 == 0:
+                buf = buf[: int(rng.integers(0, meta_end + 1))]
+            check(buf)
+    assert "ok" in seen and len(seen) >= 12, sorted(seen)  # a dozen distinct outcomes at least
 
 
 # --------------------------------------------------------------------------- container feeds (SURVEY.md §8 f4)

@@ -38,6 +38,32 @@ KERNEL(k_popc, asm volatile("popc.b32 %0, %0; or.b32 %0, %0, %1;" : "+r"(r[i]) :
 KERNEL(k_vimnmx, asm volatile("max.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b)))
 KERNEL(k_setp_sel, asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p; }" : "+r"(r[i]) : "r"(b), "r"(c)))
 
+
+// 64-bit chains: the i64 accumulate of the prediction (IMAD.WIDE) against its double-precision equivalent
+// (DFMA is exact for these products: 15-bit coefficients x 25-bit samples, sums below 2^53) and the conversions
+// the latter would need once per sample.
+#define KERNEL64(name, T, INIT, ASM)                                                                  \
+    __global__ void name(uint32_t* out, uint32_t seed, long long* cyc) {                              \
+        T r[CHAINS];                                                                                  \
+        for (int i = 0; i < CHAINS; i++) r[i] = (T)(INIT);                                            \
+        int b = (int)(seed | 5u), c = (int)((seed >> 3) | 9u);                                        \
+        double db = (double)b, dc = 1.0 / (double)c;                                                  \
+        __syncthreads();                                                                              \
+        long long t0 = clock64();                                                                     \
+        for (int it = 0; it < ITERS; it++) {                                                          \
+            _Pragma("unroll") for (int i = 0; i < CHAINS; i++) { ASM; }                               \
+        }                                                                                             \
+        long long t1 = clock64();                                                                     \
+        T s = 0;                                                                                      \
+        for (int i = 0; i < CHAINS; i++) s += r[i];                                                   \
+        out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)(long long)s + (uint32_t)(db + dc);    \
+        if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;                                              \
+    }
+KERNEL64(k_imad_wide, long long, seed + threadIdx.x * 31 + i * 7, asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(r[i]) : "r"((int)r[i]), "r"(c)))
+KERNEL64(k_dfma, double, seed + threadIdx.x * 31 + i * 7, asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(r[i]) : "d"(db), "d"(dc)))
+KERNEL64(k_cvt_rt, double, seed + threadIdx.x * 31 + i * 7,
+         { long long q; asm volatile("cvt.rzi.s64.f64 %0, %1;" : "=l"(q) : "d"(r[i])); int lo = (int)(q >> 3) + b; asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(r[i]) : "r"(lo)); })
+
 __global__ void k_lds(uint32_t* out, uint32_t seed, long long* cyc) {  // dependent shared-memory loads, conflict-free
     __shared__ uint32_t s[1024];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s[i] = (i + 32) & 1023;
@@ -93,6 +119,9 @@ int main() {
         run("VIMNMX3 (2 max fused)", k_vimnmx, threads, 0.5);
         run("SETP+SEL", k_setp_sel, threads, 2);
         run("LDS chain", k_lds, threads, 1);
+        run("IMAD.WIDE (s32xs32+s64)", k_imad_wide, threads, 1);
+        run("DFMA", k_dfma, threads, 1);
+        run("F2I.S64.F64 + I2F.F64.S32 (+shift,add)", k_cvt_rt, threads, 2);
     }
     return 0;
 }
