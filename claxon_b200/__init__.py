@@ -193,8 +193,8 @@ class Context:
 
     def __init__(self, device: int = 0, verify_crc: bool = True, n_streams: int = 2, generic_only: bool = False,
                  warp_per_frame: bool = False, lane_per_frame: bool = False, host_threads: int = 0):
-        """Default: device-resident batches and large calls use the lane-per-frame entropy kernel + lane-per-
-        subframe prediction kernel (csrc/clx_seq.cu); small synchronous host-buffer calls (latency regime) use the
+        """Default: device-resident batches and large calls use the lane-per-frame index pass + lane-per-subframe
+        decode pass (csrc/clx_fused.cu); small synchronous host-buffer calls (latency regime) use the
         warp-per-frame path (csrc/clx_coop.cu).  `warp_per_frame` / `lane_per_frame` force one of them everywhere,
         `generic_only` bypasses both (testing, A/B measurements)."""
         self._L = _lib.load()

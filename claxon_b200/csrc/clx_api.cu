@@ -98,7 +98,7 @@ struct clx_ctx {
     size_t smem_budget = 227 * 1024;
     bool use_coop = true;
     bool warp_per_frame = false;  // CLX_OPT_WARP_PER_FRAME: the warp-per-frame fast path (clx_coop.cu) everywhere
-    bool lane_per_frame_always = false;  // CLX_OPT_LANE_PER_FRAME: clx_seq.cu even for small synchronous calls
+    bool lane_per_frame_always = false;  // CLX_OPT_LANE_PER_FRAME: clx_fused.cu even for small synchronous calls
     // grow-only device scratch for clx_decode_frames, one set per stream (chunk pipelining)
     struct Scratch {
         uint8_t* d_bytes = nullptr; size_t bytes_cap = 0;
@@ -228,7 +228,7 @@ bool shape_order(const clx_frame_desc* descs, size_t lo, size_t hi, std::vector<
 }
 
 // Chooses how a set of frames maps onto the cooperative kernel (frames per CTA, shared memory).
-// Two fast paths, two regimes.  The lane-per-frame path (clx_seq.cu) has the fewest instructions per
+// Two fast paths, two regimes.  The lane-per-frame path (clx_fused.cu) has the fewest instructions per
 // sample and is what a stream of batches should use; but a lane walks its whole frame alone, so one call
 // takes ~0.4 ms of device time however few frames it holds.  A synchronous host-buffer call with a few
 // thousand frames and nothing else in flight is latency-bound: there the warp-per-frame path
@@ -251,7 +251,6 @@ clx::CoopPlan make_plan(const clx_ctx* ctx, const clx_frame_desc* descs, size_t 
     if (clx::coop_plan(max_elems, max_ch, (uint32_t)n, ctx->sm_count, ctx->smem_budget, &plan) && !ctx->warp_per_frame &&
         !(latency_call && !ctx->lane_per_frame_always)) {
         plan.G = 2;
-        plan.narrow = max_bps <= 16 ? 1u : 0u;
         plan.max_bs = max_bs;
     }
     return plan;

@@ -16,14 +16,13 @@
 
 namespace clx {
 struct CoopPlan {          // whether / how a batch uses the fast path
-    uint32_t G = 0;             // 0: generic kernel only; 1: warp per frame (clx_coop.cu); 2: lane per frame (clx_seq.cu)
+    uint32_t G = 0;             // 0: generic kernel only; 1: warp per frame (clx_coop.cu); 2: lane per frame index pass + lane per subframe decode pass (clx_fused.cu)
     uint32_t frame_stride = 0;
     uint32_t channels = 0;      // channel slots per frame (power of two >= max channels in the batch)
     size_t smem_bytes = 0;
-    uint32_t narrow = 0;        // G == 2: every frame has <= 16 bits per sample, residual scratch holds i16
     uint32_t max_bs = 0;        // G == 2: largest block size in the batch
 };
-// clx_seq.cu: `which` bit 0 = entropy kernel, bit 1 = prediction kernel (both in the product; single ones for profiling)
+// clx_fused.cu: `which` bit 0 = index pass, bit 1 = decode pass (both in the product; single ones in measurement builds)
 size_t seq_scratch_bytes(const CoopPlan& plan, uint32_t n_frames);
 cudaError_t launch_seq(const uint8_t* d_bytes, uint64_t buf_bytes, const clx_frame_desc* d_descs, uint32_t n_frames,
                        int32_t* d_out, clx_frame_result* d_results, int* d_need_generic, void* d_params,
