@@ -33,8 +33,8 @@ block size 4096, LPC order 8, Rice parameter 4, mid/side.  One *step* = one pass
   roofline — HBM: algorithmic bytes (frame bytes read once + planar i32 written once) / device
            time, against the measured copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline — the CPU oracle (a C restatement of claxon; kind "port") on all host cores.
-  workloads — at N=1, short measurements of BASELINE.json's other configurations (c3, c4, c5) by the
-           same method, bit-exactness checked against the generator's PCM.
+  workloads — at N=1, short measurements of BASELINE.json's other configurations (c3, c4, c5) and of C2's
+           independent-stereo variant by the same method, bit-exactness checked against the generator's PCM.
 
 `--impl reference` times that CPU port alone, same config/metric (the reference itself is Rust and
 cannot be built in this image or on the GPU box: no rustc / cargo on either).
@@ -520,6 +520,25 @@ def main():
 
     cpu = None
     extra = None
+    demux = None
+    if rank == 0 and n_mine:
+        # the step before the path: frame boundaries of a raw byte stream, found on the host by sync
+        # scan + CRC-8 + CRC-16 confirmation (clx_demux_frames), one thread and `host_threads` threads
+        hb0 = job.host[0][0]
+        stream_bytes = np.concatenate([hb0.data] * 8)  # 8 units back to back: ~50 MB
+        rates = {}
+        for th in (1, host_threads):
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                dd, _, _, _ = cb.demux_frames(stream_bytes, threads=th)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            assert dd.size == 8 * hb0.n_frames
+            rates[th] = stream_bytes.size / best / 1e9
+        demux = {"GBps_one_thread": rates[1], "GBps": rates[host_threads], "threads": host_threads,
+                 "Msamples_per_s": rates[host_threads] * 1e9 / (hb0.data.size / hb0.n_samples) / 1e6,
+                 "note": "clx_demux_frames_mt on the host: sync scan, header parse + CRC-8, CRC-16 of every byte"}
     if rank == 0 and world == 1:
         if args.cpu_seconds > 0 and n_mine:
             cores = os.cpu_count() or 1
@@ -539,7 +558,8 @@ def main():
             # fill the chip (c4, 1100-frame units: 48 in flight 95, 96 -> 126, 128 -> 146 Gsamples/s,
             # profiles/c4_units_in_flight_r02.txt); c5's frames are 128 times longer than their count suggests.
             cx = cb.Context(device=local, n_streams=128, host_threads=host_threads)
-            for wl, nu in (("c3", 16), ("c4", 128), ("c5", 16)):
+            # (c2-indep: SURVEY §8d asks for the independent-stereo variant of C2 next to the mid/side headline)
+            for wl, nu in (("c2-indep", 128), ("c3", 16), ("c4", 128), ("c5", 16)):
                 try:
                     extra[wl] = short_line(cb, synth, cx, wl, nu, min(128, nu))
                 except Exception as e:  # never lose the headline line to an auxiliary measurement
@@ -562,7 +582,7 @@ def main():
                                     "alone, same regime: 3.7 + 13.5 us of the step, profiles/SUMMARY_r02.md)",
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "traffic_source": (traffic or {}).get("source")},
-            "cpu_baseline": cpu, "workloads": extra,
+            "cpu_baseline": cpu, "host_demux": demux, "workloads": extra,
         }
         print(json.dumps(line))
     if dist is not None:

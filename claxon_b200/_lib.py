@@ -63,6 +63,8 @@ SYMBOLS = {
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "clx_demux_frames": (_sz, [_u8p, _sz, C.c_uint64, _vp, _sz, C.POINTER(C.c_uint64),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_uint32]),
+    "clx_demux_frames_mt": (_sz, [_u8p, _sz, C.c_uint64, _vp, _sz, C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_uint32, C.c_uint32]),
     "clx_ogg_frames": (C.c_int, [_u8p, _sz, C.POINTER(StreamInfoC), _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz),
                                  C.POINTER(C.c_uint64), C.c_uint32]),
     "clx_mp4_frames": (C.c_int, [_u8p, _sz, C.POINTER(StreamInfoC), _vp, _sz, C.POINTER(_sz), C.POINTER(C.c_uint64), C.c_uint32]),

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "claxon_b200.h"
@@ -410,6 +411,153 @@ size_t clx_demux_frames(const uint8_t* bytes, size_t n, uint64_t start, clx_fram
             descs[count++] = d;
             break;
         }
+    }
+    if (next_offset) *next_offset = pos;
+    if (total_out_elems) *total_out_elems = out_at;
+    if (stop_status) *stop_status = stop;
+    return count;
+}
+
+}  // extern "C"
+
+namespace {
+
+// The largest a frame with this header can be (every subframe verbatim, every sample wasting nothing), with slack:
+// how far a worker looks for the end of a frame whose START it is not sure of.
+size_t frame_size_bound(const clx_frame_desc& d) {
+    const size_t bps = d.bits_per_sample ? d.bits_per_sample : 32;
+    return (size_t)d.header_len + (size_t)d.n_channels * (((size_t)d.block_size * (bps + 1) + 7) / 8 + 16) + 64;
+}
+
+// One worker of clx_demux_frames_mt: the frames that START in [lo, hi), found without knowing where the stream's
+// frames begin.  Candidates are positions whose header parses (sync code, field codes, CRC-8); a candidate counts
+// once a CRC-16-confirmed end lies within the size its header allows — from there on the ordinary chain runs
+// (every boundary CRC-confirmed) until a frame starts at or after `hi`.
+struct DemuxPart {
+    uint64_t first = UINT64_MAX;       // start of the first frame of the chain (UINT64_MAX: none found)
+    uint64_t end = 0;                  // where the chain stopped: the next frame's start (>= hi), or the stop position
+    int stop = CLX_OK;                 // CLX_OK: ran into `hi`; else the status at `end` (CLX_EOF at a clean end)
+    bool open_tail = false;            // the last descriptor has an unknown boundary (sequential semantics: the last one)
+    std::vector<clx_frame_desc> descs; // out_offset not filled
+};
+
+void demux_chain(const uint8_t* bytes, size_t n, uint64_t from, uint64_t hi, uint32_t flags, DemuxPart& part) {
+    uint64_t pos = from;
+    clx_frame_desc buf[64];
+    for (;;) {
+        if (pos >= hi) { part.end = pos; part.stop = CLX_OK; return; }
+        uint64_t next = pos, total = 0;
+        int stop = CLX_OK;
+        // frames from pos, a few at a time; stops by itself at the first position that is not a frame start
+        const size_t got = clx_demux_frames(bytes, n, pos, buf, 64, &next, &total, &stop, flags);
+        for (size_t i = 0; i < got; i++) {
+            if (buf[i].byte_offset >= hi) { part.end = buf[i].byte_offset; part.stop = CLX_OK; return; }
+            part.descs.push_back(buf[i]);
+            if (!(buf[i].flags & CLX_FRAME_CRC16_VERIFIED)) {  // boundary unknown: always the last one
+                part.open_tail = true;
+                part.end = buf[i].byte_offset;
+                part.stop = CLX_OK;
+                return;
+            }
+        }
+        if (got < 64) { part.end = next; part.stop = stop == CLX_OK ? CLX_EOF : stop; return; }
+        pos = next;
+    }
+}
+
+void demux_worker(const uint8_t* bytes, size_t n, uint64_t lo, uint64_t hi, bool exact_start, uint32_t flags, DemuxPart& part) {
+    if (exact_start) {  // the caller vouches for `lo`: plain chain, errors and all
+        part.first = lo;
+        demux_chain(bytes, n, lo, hi, flags, part);
+        return;
+    }
+    for (uint64_t c = lo; c < hi && c + 2 <= n; c++) {
+        const uint8_t* nx = (const uint8_t*)memchr(bytes + c, 0xff, (size_t)(std::min<uint64_t>(hi, n - 1) - c));
+        if (!nx) break;
+        c = (uint64_t)(nx - bytes);
+        if ((bytes[c + 1] & 0xfe) != 0xf8) continue;
+        clx_frame_desc d;
+        if (clx_parse_frame_header(bytes + c, n - c, &d, flags) != CLX_OK) continue;
+        // confirm: one frame from c, looking no further than a frame with this header can reach
+        const size_t window = std::min<size_t>(n - c, frame_size_bound(d) + 16);
+        clx_frame_desc one;
+        uint64_t next = c, total = 0;
+        int stop = CLX_OK;
+        if (clx_demux_frames(bytes + c, window, 0, &one, 1, &next, &total, &stop, flags) != 1) continue;
+        if (!(one.flags & CLX_FRAME_CRC16_VERIFIED)) continue;
+        if (window < n - c && one.byte_len == window) continue;  // "confirmed" only by the window's artificial end
+        part.first = c;
+        demux_chain(bytes, n, c, hi, flags, part);
+        return;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// clx_demux_frames on `n_threads` host threads: the byte range is cut into equal parts, every worker finds the
+// frames that start in its part (see demux_worker) and the parts are stitched in order — a part is accepted only
+// if the chain before it ends exactly where it begins; otherwise (a false start that survived CRC-8 and CRC-16:
+// a 2^-24 event, or damage) the previous chain simply carries on through it.  Same results as clx_demux_frames,
+// descriptor for descriptor.
+size_t clx_demux_frames_mt(const uint8_t* bytes, size_t n, uint64_t start, clx_frame_desc* descs, size_t max_frames,
+                           uint64_t* next_offset, uint64_t* total_out_elems, int* stop_status, uint32_t flags,
+                           uint32_t n_threads) {
+    const size_t min_part = 1u << 16;
+    if (start > n) n_threads = 1;
+    size_t parts = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+    if (start <= n) parts = std::min<size_t>(parts, std::max<size_t>(1, (n - start) / min_part));
+    if (parts <= 1) return clx_demux_frames(bytes, n, start, descs, max_frames, next_offset, total_out_elems, stop_status, flags);
+    std::vector<DemuxPart> part(parts);
+    std::vector<uint64_t> cut(parts + 1);
+    for (size_t t = 0; t <= parts; t++) cut[t] = start + (uint64_t)((n - start) * t / parts);
+    {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < parts; t++)
+            th.emplace_back([&, t] { demux_worker(bytes, n, cut[t], cut[t + 1], false, flags, part[t]); });
+        demux_worker(bytes, n, cut[0], cut[1], true, flags, part[0]);
+        for (auto& x : th) x.join();
+    }
+    size_t count = 0;
+    uint64_t out_at = total_out_elems ? *total_out_elems : 0, pos = start;
+    int stop = CLX_OK;
+    bool done = false;
+    auto emit = [&](const clx_frame_desc& src) {
+        clx_frame_desc d = src;
+        const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
+        d.out_offset = out_at;
+        out_at += (elems + 3) & ~3ull;
+        descs[count++] = d;
+    };
+    for (size_t t = 0; t < parts && !done; t++) {
+        DemuxPart* p = &part[t];
+        DemuxPart redo;
+        if (t > 0 && pos >= cut[t + 1]) continue;  // the chain so far already reaches past this part
+        if (t > 0 && p->first != pos) {
+            // the part does not begin where the chain ends: let the chain carry on through it
+            redo.first = pos;
+            demux_chain(bytes, n, pos, cut[t + 1], flags, redo);
+            p = &redo;
+        }
+        for (const clx_frame_desc& d : p->descs) {
+            if (count == max_frames) { done = true; break; }
+            emit(d);
+            pos = d.byte_offset + d.byte_len;
+            if (!(d.flags & CLX_FRAME_CRC16_VERIFIED)) { pos = d.byte_offset; done = true; break; }  // unknown boundary: the last one
+        }
+        if (done) break;
+        if (count == max_frames) { done = true; break; }  // (the sequential routine does not look past its last descriptor either)
+        pos = p->end;
+        if (p->stop != CLX_OK) { stop = p->stop; done = true; }
+    }
+    if (!done && count < max_frames) {
+        // The parts are used up and nothing said stop (a chain that ran into its part's end exactly at the end of
+        // the stream, for one): whatever is left, usually nothing, goes the sequential way, which also names the
+        // status at the position where it ends.
+        uint64_t total = out_at;
+        count += clx_demux_frames(bytes, n, pos, descs + count, max_frames - count, &pos, &total, &stop, flags);
+        out_at = total;
     }
     if (next_offset) *next_offset = pos;
     if (total_out_elems) *total_out_elems = out_at;

@@ -130,6 +130,15 @@ size_t clx_demux_frames(const uint8_t* bytes, size_t n, uint64_t start, clx_fram
                         size_t max_frames, uint64_t* next_offset, uint64_t* total_out_elems,
                         int* stop_status, uint32_t flags);
 
+/* The same on `n_threads` host threads (0 = one per hardware thread): the byte range is cut into equal parts, every
+ * worker finds the frames that START in its part — a start counts once its header parses (sync code, field codes,
+ * CRC-8) and a CRC-16-confirmed end lies within the size that header allows — and the parts are stitched in order,
+ * a part being accepted only if the chain before it ends exactly where it begins.  Descriptor for descriptor the
+ * result of clx_demux_frames; the scan (dominated by the CRC-16 of every byte) runs at n_threads times its rate. */
+size_t clx_demux_frames_mt(const uint8_t* bytes, size_t n, uint64_t start, clx_frame_desc* descs,
+                           size_t max_frames, uint64_t* next_offset, uint64_t* total_out_elems,
+                           int* stop_status, uint32_t flags, uint32_t n_threads);
+
 /* Container feeds: a wrapper that stores one FLAC frame per packet / sample hands over
  * the frame boundaries, so no search (clx_demux_frames) is needed.  What the reference leaves to the `ogg`
  * and `mp4parse` crates in examples/decode_ogg.rs:26-125 and examples/decode_mp4.rs:26-167.

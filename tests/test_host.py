@@ -262,6 +262,60 @@ def test_demux_false_sync_inside_residual_is_rejected():
     assert descs.size >= 3 and not (descs["flags"][-1] & cb.FRAME_CRC16_VERIFIED) or descs.size == b.n_frames
 
 
+def _same_demux(a, b):
+    return a[0].size == b[0].size and np.array_equal(a[0], b[0]) and tuple(a[1:]) == tuple(b[1:])
+
+
+def test_demux_on_several_threads_equals_sequential():
+    """clx_demux_frames_mt (parts of the byte range on host threads, stitched by CRC-16-confirmed chains) returns
+    descriptor for descriptor what clx_demux_frames returns: clean streams of every workload shape, a metadata prefix,
+    planted sync codes with a valid-looking header, damaged frames (unknown boundary: the last descriptor), garbage
+    between frames (stop status), truncation, and the max_frames limit."""
+    L = _lib.load()
+    rng = np.random.default_rng(31)
+    cases = []
+    for wl, n in (("c2", 96), ("c3", 64), ("c4", 110), ("c5", 6)):
+        b = synth.workload(wl, n)
+        cases.append((f"{wl} clean", b.data.copy(), 0))
+        d = b.data.copy()
+        d[int(b.frame_offsets[n // 2]) + 40] ^= 0x20             # a damaged frame in the middle
+        cases.append((f"{wl} damaged", d, 0))
+        cases.append((f"{wl} truncated", b.data[: int(b.frame_offsets[n - 2]) + 11].copy(), 0))
+        d = np.concatenate([b.data[: int(b.frame_offsets[n // 3])], np.frombuffer(b"\x00garbage\xff\xf8\x00\x00", np.uint8),
+                            b.data[int(b.frame_offsets[n // 3]):]])
+        cases.append((f"{wl} garbage between frames", d, 0))
+        # planted false starts: a real frame header (so sync, codes and CRC-8 are all right) copied into residual data
+        d = b.data.copy()
+        hdr = d[int(b.frame_offsets[1]): int(b.frame_offsets[1]) + 8].copy()
+        for i in range(2, n, 3):
+            at = int(b.frame_offsets[i]) + int(b.frame_lengths[i]) // 2
+            d[at: at + hdr.size] = hdr
+            # keep the frame intact as far as its CRC-16 goes: patch the footer
+            f0, f1 = int(b.frame_offsets[i]), int(b.frame_offsets[i + 1])
+            c = L.clx_crc16(d[f0: f1 - 2].tobytes(), f1 - 2 - f0)
+            d[f1 - 2], d[f1 - 1] = c >> 8, c & 0xff
+        cases.append((f"{wl} planted headers", d, 0))
+    fb = synth.workload("c4", 44)
+    file_bytes = np.frombuffer(synth.make_file(fb, 0, 44, padding=300), np.uint8)
+    si, first = cb.open_stream(file_bytes)
+    cases.append(("file with metadata", file_bytes.copy(), first))
+    for name, data, start in cases:
+        ref = cb.demux_frames(data, start=start)
+        assert ref[0].size > 0, name
+        for th in (2, 3, 5, 8, 13):
+            got = cb.demux_frames(data, start=start, threads=th)
+            assert _same_demux(ref, got), (name, th, ref[0].size, got[0].size, ref[1:], got[1:])
+        for cap in (1, 7, ref[0].size):
+            a = cb.demux_frames(data, start=start, max_frames=cap)
+            g = cb.demux_frames(data, start=start, max_frames=cap, threads=4)
+            assert _same_demux(a, g), (name, "max_frames", cap)
+    # parts smaller than a frame, parts that start inside the last frame, a start offset past the end
+    b = synth.workload("c5", 3)
+    ref = cb.demux_frames(b.data)
+    assert _same_demux(ref, cb.demux_frames(b.data, threads=8))
+    assert cb.demux_frames(b.data, start=b.data.size + 5, threads=4)[0].size == 0
+
+
 def test_block_api_matches_reference_unit_tests():
     k = KAT["block_sample"]
     blk = cb.Block(0, k["block_size"], np.array(k["buffer"], dtype=np.int32))
