@@ -58,6 +58,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         LIB = os.path.join(HERE, "libclaxon_b200_exp.so")
     if os.environ.get("CLX_RING_TMA"):
         LIB = LIB.replace(".so", "_tma.so")
+    if os.environ.get("CLX_DEC_WARPS"):
+        LIB = LIB.replace(".so", "_w" + str(int(os.environ["CLX_DEC_WARPS"])) + ".so")
     if not force and not _newer(LIB, lib_deps()):
         return LIB
     nvcc = nvcc_path()
@@ -70,6 +72,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         extra.append("-DCLX_EXPERIMENT")
     if os.environ.get("CLX_RING_TMA"):
         extra.append("-DCLX_RING_TMA")
+    if os.environ.get("CLX_DEC_WARPS"):
+        extra.append("-DCLX_DEC_WARPS=" + str(int(os.environ["CLX_DEC_WARPS"])))
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB, *lib_sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

@@ -297,7 +297,10 @@ index_frames_kernel(const uint8_t* __restrict__ bytes, uint64_t buf_bytes, const
 // ---------------------------------------------------------------------------------
 // Kernel 2: entropy decode + prediction + wasted shift + decorrelation, one lane per subframe
 // ---------------------------------------------------------------------------------
-constexpr int DEC_WARPS = 2;
+#ifndef CLX_DEC_WARPS
+#define CLX_DEC_WARPS 2  // warps per decode CTA (1 and 4 were measured too: profiles/SUMMARY_r02.md)
+#endif
+constexpr int DEC_WARPS = CLX_DEC_WARPS;
 constexpr uint32_t DEC_RQ = 8;
 #ifdef CLX_RING_TMA
 using SubIO = TmaIO<64>;
