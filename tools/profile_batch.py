@@ -1,5 +1,5 @@
 """Decodes one device-resident batch a few times (target for ncu): python tools/profile_batch.py <workload> <frames> <reps> [lane].
-`lane`: force the lane-per-frame throughput path (frames with very long index walks default to the warp-per-frame path)."""
+`lane`: force the lane-per-frame throughput path (it is what device-resident batches use anyway)."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
