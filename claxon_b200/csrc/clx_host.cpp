@@ -513,16 +513,31 @@ size_t clx_demux_frames_mt(const uint8_t* bytes, size_t n, uint64_t start, clx_f
     std::vector<uint64_t> cut(parts + 1);
     for (size_t t = 0; t <= parts; t++) cut[t] = start + (uint64_t)((n - start) * t / parts);
     {
+        // No exception may cross the C ABI: a thread that cannot be started (resource limits) just leaves its part to
+        // the stitching pass, which then walks through it sequentially; an allocation failure anywhere falls back to
+        // the sequential routine altogether.
         std::vector<std::thread> th;
-        for (size_t t = 1; t < parts; t++)
-            th.emplace_back([&, t] { demux_worker(bytes, n, cut[t], cut[t + 1], false, flags, part[t]); });
-        demux_worker(bytes, n, cut[0], cut[1], true, flags, part[0]);
+        bool failed = false;
+        try {
+            th.reserve(parts);
+            for (size_t t = 1; t < parts; t++) {
+                try {
+                    th.emplace_back([&, t] {
+                        try { demux_worker(bytes, n, cut[t], cut[t + 1], false, flags, part[t]); }
+                        catch (...) { part[t] = DemuxPart(); }
+                    });
+                } catch (...) { break; }
+            }
+            demux_worker(bytes, n, cut[0], cut[1], true, flags, part[0]);
+        } catch (...) { failed = true; }
         for (auto& x : th) x.join();
+        if (failed) return clx_demux_frames(bytes, n, start, descs, max_frames, next_offset, total_out_elems, stop_status, flags);
     }
     size_t count = 0;
     uint64_t out_at = total_out_elems ? *total_out_elems : 0, pos = start;
     int stop = CLX_OK;
     bool done = false;
+    try {
     auto emit = [&](const clx_frame_desc& src) {
         clx_frame_desc d = src;
         const uint64_t elems = (uint64_t)d.n_channels * d.block_size;
@@ -558,6 +573,9 @@ size_t clx_demux_frames_mt(const uint8_t* bytes, size_t n, uint64_t start, clx_f
         uint64_t total = out_at;
         count += clx_demux_frames(bytes, n, pos, descs + count, max_frames - count, &pos, &total, &stop, flags);
         out_at = total;
+    }
+    } catch (...) {  // (an allocation failed while stitching: *total_out_elems is still untouched)
+        return clx_demux_frames(bytes, n, start, descs, max_frames, next_offset, total_out_elems, stop_status, flags);
     }
     if (next_offset) *next_offset = pos;
     if (total_out_elems) *total_out_elems = out_at;
