@@ -134,6 +134,11 @@ struct DeviceIO {
 // Device IO policy of a lane, TMA flavour: a ring of two CHUNK-byte halves in shared memory, each filled by
 // one bulk copy (`cp.async.bulk`, SASS UBLKCP) that signals the half's own mbarrier
 // ---------------------------------------------------------------------------------
+// MEASUREMENT BUILD ONLY (-DCLX_RING_TMA, CLX_RING_TMA=1 in claxon_b200/_build.py): bit-exact (all GPU parity
+// tests pass with it) but 18 % slower than the cp.async ring above — a bulk copy takes uniform-register operands,
+// so the compiler serves 32 lanes with 32 sources through a loop of ~9 instructions per lane, against one LDGSTS
+// for the whole warp (profiles/ab_ring_tma_r02.json vs ab_ring_cpasync_r02.json).  Kept so that the comparison can
+// be repeated; the product library is built without it.
 // Chunk c of the frame (CHUNK bytes from its 16-byte aligned base) lives in half c & 1.  A half is re-armed
 // only after the cursor has left the chunk it held, so at most one copy per half is ever outstanding and the
 // parity to wait for simply alternates.  Reads past the end of the byte buffer see the buffer's last chunk
