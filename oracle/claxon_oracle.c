@@ -5,6 +5,15 @@
  * one-byte cache (`Bitstream{data,bits_left}`): only the observable semantics of
  * src/input.rs:415-643 are kept (MSB-first fields; a read fails with
  * UnexpectedEof exactly when it needs a bit past the end of the input).
+ *
+ * PARITY PINNED: against every in-source known-answer vector of the reference's unit tests on
+ * this path (tests/golden/kat.json, tests/test_oracle_golden.py), against the STREAMINFO MD5 of
+ * pop.flac / short.flac / wasted_bits.flac and the two Vorbis-comment variants
+ * (tests/golden/fixtures.npz), against the reference's fuzz corpus statuses, and — for the shapes
+ * no fixture reaches — frame by frame against a second, independent restatement in plain Python
+ * (tests/spec_decode.py, tests/spec_header.py, tests/spec_metadata.py).  The reference itself is
+ * Rust; neither the authoring image nor the GPU box has rustc / cargo, so there is no oracle/_ref.
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU arms may call this code.
  */
 #include "claxon_oracle.h"
 
